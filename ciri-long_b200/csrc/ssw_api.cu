@@ -1,0 +1,514 @@
+// ssw_api.cu -- host side of libssw_cuda.so: the C ABI of include/ssw_cuda.h.
+//
+// Batched interface: ssw_batch_create uploads the struct-of-arrays batch, ssw_batch_run enqueues the
+// whole hot path on one stream without any host round trip (work lists, counts and cursors live in
+// device memory), ssw_batch_fetch synchronises and copies results + CIGARs back.
+// Legacy interface: the six symbols of the reference libssw.so (ssw.h:72-182) as a batch of one pair.
+// There is no CPU implementation of the alignment in this file or behind it.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/ssw_cuda.h"
+#include "ssw_common.cuh"
+#include "ssw_kernels.h"
+
+using namespace sswb;
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+extern "C" const char* ssw_cuda_last_error(void) { return g_last_error.c_str(); }
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+            return SSW_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+static const int LONG_REF_THRESHOLD = 32768;          // references longer than this get their own scratch class
+static const long long SCRATCH_BUDGET = 3LL << 30;    // bytes of score-pass scratch per class
+
+struct ssw_batch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int32_t n = 0;
+    int sms = 0;
+    Scoring sc;
+    // inputs
+    int8_t* d_seqs = nullptr;
+    long long *d_qoff = nullptr, *d_roff = nullptr;
+    int32_t *d_qlen = nullptr, *d_rlen = nullptr, *d_mask = nullptr;
+    PairRec* d_rec = nullptr;
+    // lists: [count | base | fill | cursor | count2 | cursor2] x N_LISTS
+    int32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_meta = nullptr;
+    // scratch
+    unsigned char* d_sscr[2] = {nullptr, nullptr};
+    long long sstride[2] = {0, 0}, off_col[2] = {0, 0}, off_bnd[2] = {0, 0}, off_snap[2] = {0, 0};
+    int sblocks[2] = {0, 0};
+    unsigned char* d_bscr = nullptr;
+    long long bstride = 0, bdir = 0;
+    int bblocks = 0, bstage = 0;
+    uint32_t* d_cigar = nullptr;
+    long long cigar_cap = 0;
+    unsigned long long* d_cigar_used = nullptr;
+    // host-side shape summary
+    int max_q = 0, max_r = 0, maxK = 0;
+    bool have[2][2][KMAX + 1];           // forward lists known to be non-empty: [cls][kind][K]
+    int64_t launches = 0;
+    std::vector<PairRec> h_rec;
+
+    BatchView view() const { return BatchView{d_seqs, d_qoff, d_qlen, d_roff, d_rlen, d_mask, d_rec, n}; }
+    ListSet lists() const { return ListSet{d_idx, d_meta, d_meta + N_LISTS, d_meta + 2 * N_LISTS, d_meta + 3 * N_LISTS}; }
+    int32_t* count2() const { return d_meta + 4 * N_LISTS; }
+    int32_t* cursor2() const { return d_meta + 5 * N_LISTS; }
+};
+
+static int host_strip_height(int m) { return m <= VSTRIPS * KMAX ? (m + VSTRIPS - 1) / VSTRIPS : KMAX; }
+
+// Which scoring schemes the device recurrences reproduce bit-exactly (see ssw_score.cu header):
+// 5x5 matrix with a zero N row/column (the only matrix ssw_wrap.py:146-159 builds), gap_open >=
+// gap_extend >= 1 and 2*gap_extend >= the largest mismatch penalty (an insertion next to a deletion is
+// then never better than substitutions, which makes the reference's lazy-F bookkeeping unobservable).
+static bool scoring_supported(const ssw_scoring* s, std::string* why)
+{
+    int minv = 0;
+    for (int k = 0; k < 25; ++k) minv = std::min<int>(minv, s->mat[k]);
+    for (int k = 0; k < 5; ++k)
+        if (s->mat[4 * 5 + k] != 0 || s->mat[k * 5 + 4] != 0) { *why = "N row/column of the matrix must be zero"; return false; }
+    if (s->gap_extend < 1 || s->gap_open < s->gap_extend) { *why = "need gap_open >= gap_extend >= 1"; return false; }
+    if (2 * (int)s->gap_extend < -minv) { *why = "need 2*gap_extend >= largest mismatch penalty"; return false; }
+    if (s->gap_open > 100 || -minv > 100) { *why = "penalties above 100 are not supported"; return false; }
+    return true;
+}
+
+extern "C" void ssw_batch_destroy(ssw_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_seqs); cudaFree(b->d_qoff); cudaFree(b->d_roff); cudaFree(b->d_qlen); cudaFree(b->d_rlen);
+    cudaFree(b->d_mask); cudaFree(b->d_rec); cudaFree(b->d_idx); cudaFree(b->d_idx2); cudaFree(b->d_meta);
+    cudaFree(b->d_sscr[0]); cudaFree(b->d_sscr[1]); cudaFree(b->d_bscr); cudaFree(b->d_cigar); cudaFree(b->d_cigar_used);
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const int64_t* q_off, const int32_t* q_len,
+                       const int64_t* r_off, const int32_t* r_len, const int32_t* mask_len)
+{
+    const int32_t n = b->n;
+    std::vector<int32_t> mask(n);
+    memset(b->have, 0, sizeof b->have);
+    int maxScore = 0;
+    for (int k = 0; k < 25; ++k) maxScore = std::max<int>(maxScore, b->sc.mat[k]);
+    long long cig_cap = 16;
+    for (int32_t p = 0; p < n; ++p) {
+        const int m = q_len[p], r = r_len[p];
+        if (m < 0 || r < 0 || q_off[p] < 0 || r_off[p] < 0 || q_off[p] + m > seqs_len || r_off[p] + r > seqs_len) {
+            set_error("pair " + std::to_string(p) + ": offsets/lengths outside the sequence buffer");
+            return SSW_ERR_ARG;
+        }
+        mask[p] = mask_len ? mask_len[p] : (m > 30 ? m / 2 : 15);          // ssw_wrap.py:196-199
+        b->max_q = std::max(b->max_q, m);
+        b->max_r = std::max(b->max_r, r);
+        if (m > 0 && r > 0) {
+            const int K = host_strip_height(m);
+            const int kind = (b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255) ? 1 : 0;
+            b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
+            b->maxK = std::max(b->maxK, K);
+            cig_cap += 2LL * m + 3;
+        }
+    }
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, b->device));
+    b->sms = prop.multiProcessorCount;
+
+    const size_t nn = (size_t)std::max(n, 1);
+    CU_TRY(cudaMalloc(&b->d_seqs, (size_t)std::max<int64_t>(seqs_len, 1)));
+    CU_TRY(cudaMalloc(&b->d_qoff, nn * 8)); CU_TRY(cudaMalloc(&b->d_roff, nn * 8));
+    CU_TRY(cudaMalloc(&b->d_qlen, nn * 4)); CU_TRY(cudaMalloc(&b->d_rlen, nn * 4)); CU_TRY(cudaMalloc(&b->d_mask, nn * 4));
+    CU_TRY(cudaMalloc(&b->d_rec, nn * sizeof(PairRec)));
+    CU_TRY(cudaMalloc(&b->d_idx, nn * 4)); CU_TRY(cudaMalloc(&b->d_idx2, nn * 4));
+    CU_TRY(cudaMalloc(&b->d_meta, 6 * N_LISTS * 4));
+    CU_TRY(cudaMalloc(&b->d_cigar_used, 8));
+    CU_TRY(cudaMemcpyAsync(b->d_seqs, seqs, (size_t)seqs_len, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_qoff, q_off, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_roff, r_off, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_qlen, q_len, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_rlen, r_len, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_mask, mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));       // `mask` is a local; the user buffers may be pageable
+
+    // score-pass scratch: class 0 = references up to LONG_REF_THRESHOLD columns, class 1 = longer ones
+    for (int cls = 0; cls < 2; ++cls) {
+        bool any = false;
+        for (int kind = 0; kind < 2; ++kind) for (int K = 1; K <= KMAX; ++K) any |= b->have[cls][kind][K];
+        if (!any) continue;
+        const int ncap = cls == 0 ? std::min(b->max_r, LONG_REF_THRESHOLD) : b->max_r;
+        b->sstride[cls] = score_scratch_layout(ncap, &b->off_col[cls], &b->off_bnd[cls], &b->off_snap[cls]);
+        long long blocks = SCRATCH_BUDGET / (b->sstride[cls] * SCORE_WARPS);
+        blocks = std::max<long long>(1, std::min<long long>(blocks, b->sms));
+        blocks = std::min<long long>(blocks, (n + SCORE_WARPS - 1) / SCORE_WARPS);
+        b->sblocks[cls] = (int)blocks;
+        CU_TRY(cudaMalloc(&b->d_sscr[cls], (size_t)(blocks * SCORE_WARPS * b->sstride[cls])));
+    }
+    // CIGAR stage scratch and output
+    if (b->sc.flag != 0) {
+        b->bstage = b->max_q + b->max_r + 16;
+        b->bdir = std::min<long long>(std::max<long long>(65536, 192LL * std::min(b->max_q, b->max_r + b->max_q)), 16LL << 20);
+        b->bstride = ((long long)b->bstage * 4 + b->bdir + 255) & ~255LL;
+        long long blocks = std::min<long long>((long long)b->sms * 2, (n + BAND_WARPS - 1) / BAND_WARPS);
+        blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->bstride * BAND_WARPS)));
+        b->bblocks = (int)blocks;
+        CU_TRY(cudaMalloc(&b->d_bscr, (size_t)(blocks * BAND_WARPS * b->bstride)));
+        b->cigar_cap = cig_cap;
+        CU_TRY(cudaMalloc(&b->d_cigar, (size_t)cig_cap * 4));
+    }
+    return SSW_OK;
+}
+
+extern "C" ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                                       const int64_t* q_off, const int32_t* q_len, const int64_t* r_off,
+                                       const int32_t* r_len, const int32_t* mask_len, const ssw_scoring* scoring)
+{
+    if (n_pairs < 0 || !scoring || (n_pairs > 0 && (!seqs || !q_off || !q_len || !r_off || !r_len))) {
+        set_error("ssw_batch_create: invalid argument");
+        return nullptr;
+    }
+    std::string why;
+    if (!scoring_supported(scoring, &why)) {
+        set_error("scoring scheme not supported by the device kernels: " + why);
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        set_error("no usable CUDA device (libssw_cuda has no CPU path)");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    ssw_batch* b = new ssw_batch();
+    b->device = device;
+    b->n = n_pairs;
+    memcpy(b->sc.mat, scoring->mat, 25);
+    b->sc.go = scoring->gap_open; b->sc.ge = scoring->gap_extend;
+    int minv = 0;
+    for (int k = 0; k < 25; ++k) minv = std::min<int>(minv, scoring->mat[k]);
+    b->sc.bias = -minv;                                                  // ssw.c:756-762
+    b->sc.flag = scoring->flag; b->sc.filters = scoring->filters; b->sc.filterd = scoring->filterd;
+    if (stream) b->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream"); delete b; return nullptr; }
+        b->own_stream = true;
+    }
+    if (batch_alloc(b, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len) != SSW_OK) { ssw_batch_destroy(b); return nullptr; }
+    return b;
+}
+
+extern "C" int ssw_batch_run(ssw_batch* b)
+{
+    if (!b) return SSW_ERR_ARG;
+    CU_TRY(cudaSetDevice(b->device));
+    if (b->n == 0) return SSW_OK;
+    cudaStream_t st = b->stream;
+    int launches = 0;
+    const BatchView view = b->view();
+    const ListSet ls = b->lists();
+    CU_TRY(cudaMemsetAsync(b->d_cigar_used, 0, 8, st));
+    CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
+
+    auto score_args = [&](int cls) {
+        ScoreArgs a;
+        a.b = view; a.sc = b->sc;
+        a.scratch = b->d_sscr[cls]; a.scratch_stride = b->sstride[cls];
+        a.off_col = b->off_col[cls]; a.off_bnd = b->off_bnd[cls]; a.off_snap = b->off_snap[cls];
+        a.rerun = 0; a.next_idx = nullptr; a.next_base = nullptr; a.next_count = nullptr;
+        return a;
+    };
+
+    // ---- forward pass
+    CU_TRY(build_lists(0, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
+    for (int cls = 0; cls < 2; ++cls)
+        for (int kind = 0; kind < 2; ++kind)
+            for (int K = 1; K <= KMAX; ++K) {
+                if (!b->have[cls][kind][K]) continue;
+                const int id = list_id(cls, kind, K);
+                ScoreArgs a = score_args(cls);
+                a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
+                if (kind == 1) { a.next_idx = b->d_idx2; a.next_base = ls.base + id; a.next_count = b->count2() + id; }
+                CU_TRY(launch_score(K, kind == 1, false, a, b->sblocks[cls], st));
+                ++launches;
+            }
+    // ---- deciding byte-flavour pass for pairs whose truncated-F pass stayed below the 8-bit limit
+    for (int cls = 0; cls < 2; ++cls)
+        for (int K = 1; K <= KMAX; ++K) {
+            if (!b->have[cls][1][K]) continue;
+            const int id = list_id(cls, 1, K);
+            ScoreArgs a = score_args(cls);
+            a.wl = WorkList{b->d_idx2, ls.base + id, b->count2() + id, b->cursor2() + id};
+            a.rerun = 1;
+            CU_TRY(launch_score(K, false, false, a, b->sblocks[cls], st));
+            ++launches;
+        }
+    if (b->sc.flag != 0) {
+        // ---- reverse pass: strip height follows the read prefix, so any K up to the forward maximum can occur
+        CU_TRY(build_lists(1, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
+        for (int cls = 0; cls < 2; ++cls) {
+            if (!b->d_sscr[cls]) continue;
+            for (int kind = 0; kind < 2; ++kind) {
+                if (kind == 1 && b->sc.go != b->sc.ge) continue;
+                for (int K = 1; K <= b->maxK; ++K) {
+                    const int id = list_id(cls, kind, K);
+                    ScoreArgs a = score_args(cls);
+                    a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
+                    CU_TRY(launch_score(K, kind == 1, true, a, b->sblocks[cls], st));
+                    ++launches;
+                }
+            }
+        }
+        // ---- CIGAR pass
+        CU_TRY(build_band_list(view, b->sc, ls, st, &launches));
+        BandArgs ba;
+        ba.b = view; ba.sc = b->sc;
+        ba.wl = WorkList{ls.idx, nullptr, ls.count, ls.cursor};
+        ba.scratch = b->d_bscr; ba.scratch_stride = b->bstride; ba.dir_bytes = b->bdir;
+        ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap;
+        ba.cigar_used = b->d_cigar_used;
+        CU_TRY(launch_band(ba, b->bblocks, st));
+        ++launches;
+    }
+    b->launches = launches;
+    return SSW_OK;
+}
+
+extern "C" int64_t ssw_batch_launch_count(const ssw_batch* b) { return b ? b->launches : 0; }
+
+// Pairs whose direction matrix did not fit the per-warp scratch are re-run one list at a time with a
+// scratch sized for the widest band the reference could reach (band < 2*readLen, ssw.c:632).
+static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
+{
+    cudaStream_t st = b->stream;
+    long long need = 0;
+    for (int32_t p : big) {
+        const PairRec& r = b->h_rec[p];
+        const long long readLen = r.read_end1 - r.read_begin1 + 1;
+        need = std::max(need, (4 * readLen + 1) * readLen + (4 * readLen + 8) * 8 + 64);
+    }
+    const long long stride = ((long long)b->bstage * 4 + need + 255) & ~255LL;
+    long long warps = std::max<long long>(1, std::min<long long>((6LL << 30) / stride, (long long)big.size()));
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((warps + BAND_WARPS - 1) / BAND_WARPS, b->sms));
+    unsigned char* scr = nullptr;
+    CU_TRY(cudaMalloc(&scr, (size_t)(stride * blocks * BAND_WARPS)));
+    const ListSet ls = b->lists();
+    const int32_t cnt = (int32_t)big.size();
+    for (int32_t p : big) b->h_rec[p].status &= ~PS_BAND_SCRATCH;
+    std::vector<int32_t> zeros(N_LISTS, 0);
+    CU_TRY(cudaMemcpyAsync(ls.idx, big.data(), big.size() * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ls.cursor, zeros.data(), N_LISTS * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(ls.count, &cnt, 4, cudaMemcpyHostToDevice, st));
+    // clear the flag on the device records too
+    for (int32_t p : big)
+        CU_TRY(cudaMemcpyAsync(&b->d_rec[p].status, &b->h_rec[p].status, 4, cudaMemcpyHostToDevice, st));
+    BandArgs ba;
+    ba.b = b->view(); ba.sc = b->sc;
+    ba.wl = WorkList{ls.idx, nullptr, ls.count, ls.cursor};
+    ba.scratch = scr; ba.scratch_stride = stride; ba.dir_bytes = need;
+    ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap; ba.cigar_used = b->d_cigar_used;
+    CU_TRY(launch_band(ba, blocks, st));
+    b->launches += 1;
+    for (int32_t p : big)
+        CU_TRY(cudaMemcpyAsync(&b->h_rec[p], &b->d_rec[p], sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(scr);
+    return SSW_OK;
+}
+
+extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used)
+{
+    if (!b || (!out && b->n > 0)) return SSW_ERR_ARG;
+    CU_TRY(cudaSetDevice(b->device));
+    if (cigar_used) *cigar_used = 0;
+    if (b->n == 0) return SSW_OK;
+    cudaStream_t st = b->stream;
+    b->h_rec.resize(b->n);
+    CU_TRY(cudaMemcpyAsync(b->h_rec.data(), b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (b->sc.flag != 0) {
+        std::vector<int32_t> big;
+        for (int32_t p = 0; p < b->n; ++p) if (b->h_rec[p].status & PS_BAND_SCRATCH) big.push_back(p);
+        if (!big.empty()) { const int rc = rerun_big_bands(b, big); if (rc != SSW_OK) return rc; }
+    }
+    unsigned long long used = 0;
+    if (b->sc.flag != 0) {
+        CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if (cigar_used) *cigar_used = (int64_t)used;
+        if ((long long)used > b->cigar_cap) { set_error("internal cigar buffer exhausted"); return SSW_ERR_CIGAR_CAP; }
+        if (used > 0) {
+            if (!cigar_buf || (int64_t)used > cigar_cap) { set_error("cigar buffer too small"); return SSW_ERR_CIGAR_CAP; }
+            CU_TRY(cudaMemcpyAsync(cigar_buf, b->d_cigar, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    for (int32_t p = 0; p < b->n; ++p) {
+        const PairRec& r = b->h_rec[p];
+        ssw_result& o = out[p];
+        o.score1 = r.score1; o.score2 = r.score2;
+        o.ref_begin1 = r.ref_begin1; o.ref_end1 = r.ref_end1;
+        o.read_begin1 = r.read_begin1; o.read_end1 = r.read_end1; o.ref_end2 = r.ref_end2;
+        o.cigar_len = r.cigar_len; o.cigar_off = r.cigar_off; o.word = r.word;
+        if (r.status & (PS_PUNT | PS_UNSUPPORTED | PS_NEED_GOTOH | PS_BAND_SCRATCH | PS_CIGAR_CAP)) o.status = SSW_PAIR_UNSUPPORTED;
+        else if (r.status & PS_TRACEBACK_ERR) o.status = SSW_PAIR_TRACEBACK_ERR;
+        else o.status = SSW_PAIR_OK;
+        o.status |= r.status << 8;          // internal stage bits, for diagnostics (see ssw_cuda.h)
+    }
+    return SSW_OK;
+}
+
+extern "C" int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len, const int64_t* q_off,
+                               const int32_t* q_len, const int64_t* r_off, const int32_t* r_len, const int32_t* mask_len,
+                               const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap,
+                               int64_t* cigar_used)
+{
+    ssw_batch* b = ssw_batch_create(device, nullptr, n_pairs, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len, scoring);
+    if (!b) return g_last_error.find("not supported") != std::string::npos ? SSW_ERR_UNSUPPORTED
+                 : (g_last_error.find("no usable CUDA") != std::string::npos ? SSW_ERR_NODEVICE : SSW_ERR_ARG);
+    int rc = ssw_batch_run(b);
+    if (rc == SSW_OK) rc = ssw_batch_fetch(b, out, cigar_buf, cigar_cap, cigar_used);
+    ssw_batch_destroy(b);
+    return rc;
+}
+
+extern "C" void ssw_encode_dna(const char* ascii, int64_t len, int8_t* codes)
+{
+    static int8_t lut[256];
+    static bool init = false;
+    if (!init) {
+        memset(lut, 4, sizeof lut);
+        const char* bases = "ACGTN";
+        for (int k = 0; k < 5; ++k) { lut[(unsigned char)bases[k]] = (int8_t)k; lut[(unsigned char)(bases[k] + 32)] = (int8_t)k; }
+        init = true;
+    }
+    for (int64_t k = 0; k < len; ++k) codes[k] = lut[(unsigned char)ascii[k]];
+}
+
+extern "C" int ssw_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int ssw_cuda_dpx_peak(int device, double* lane_instr_per_s, double* sm_clock_mhz)
+{
+    CU_TRY(cudaSetDevice(device));
+    int khz = 0;
+    CU_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+    CU_TRY(dpx_peak_probe(lane_instr_per_s, 0));
+    return SSW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// legacy six-symbol ABI (ssw.h): a batch of one
+
+struct _profile {
+    const int8_t* read;
+    const int8_t* mat;
+    int32_t readLen;
+    int32_t n;
+    int8_t score_size;
+};
+
+extern "C" s_profile* ssw_init(const int8_t* read, const int32_t readLen, const int8_t* mat, const int32_t n,
+                               const int8_t score_size)
+{
+    s_profile* p = (s_profile*)calloc(1, sizeof(struct _profile));
+    if (!p) return nullptr;
+    p->read = read; p->mat = mat; p->readLen = readLen; p->n = n; p->score_size = score_size;
+    return p;
+}
+
+extern "C" void init_destroy(s_profile* p) { free(p); }
+
+extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t refLen, const uint8_t weight_gapO,
+                              const uint8_t weight_gapE, const uint8_t flag, const uint16_t filters,
+                              const int32_t filterd, const int32_t maskLen)
+{
+    if (!prof || !prof->read || !prof->mat) {
+        fprintf(stderr, "Please call the function ssw_init before ssw_align.\n");
+        return nullptr;
+    }
+    if (maskLen < 15)
+        fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+    if (prof->n != 5 || prof->score_size != 2) {
+        fprintf(stderr, "libssw_cuda: only the 5-letter DNA alphabet with score_size 2 (the ssw_wrap.py call) is implemented on the device.\n");
+        return nullptr;
+    }
+    if (prof->readLen <= 0 || refLen <= 0) {
+        fprintf(stderr, "libssw_cuda: empty read or reference.\n");
+        return nullptr;
+    }
+    ssw_scoring sc;
+    memset(&sc, 0, sizeof sc);
+    memcpy(sc.mat, prof->mat, 25);
+    sc.gap_open = weight_gapO; sc.gap_extend = weight_gapE; sc.flag = flag; sc.filters = filters; sc.filterd = filterd;
+    std::vector<int8_t> seqs((size_t)prof->readLen + refLen);
+    memcpy(seqs.data(), prof->read, prof->readLen);
+    memcpy(seqs.data() + prof->readLen, ref, refLen);
+    const int64_t q_off = 0, r_off = prof->readLen;
+    const int32_t q_len = prof->readLen, r_len = refLen, mask = maskLen;
+    ssw_result res;
+    std::vector<uint32_t> cig(2 * (size_t)prof->readLen + 16);
+    int64_t used = 0;
+    const int rc = ssw_align_batch(0, 1, seqs.data(), (int64_t)seqs.size(), &q_off, &q_len, &r_off, &r_len, &mask, &sc,
+                                   &res, cig.data(), (int64_t)cig.size(), &used);
+    if (rc != SSW_OK) {
+        fprintf(stderr, "libssw_cuda: %s\n", g_last_error.c_str());
+        return nullptr;
+    }
+    if ((res.status & 0xff) == SSW_PAIR_TRACEBACK_ERR) {
+        fprintf(stderr, "Trace back error.\n");
+        return nullptr;
+    }
+    if ((res.status & 0xff) != SSW_PAIR_OK) {
+        fprintf(stderr, "libssw_cuda: this pair needs a code path the device library does not provide.\n");
+        return nullptr;
+    }
+    s_align* r = (s_align*)calloc(1, sizeof(s_align));
+    r->score1 = (uint16_t)res.score1; r->score2 = (uint16_t)res.score2;
+    r->ref_begin1 = res.ref_begin1; r->ref_end1 = res.ref_end1;
+    r->read_begin1 = res.read_begin1; r->read_end1 = res.read_end1; r->ref_end2 = res.ref_end2;
+    r->cigar = nullptr; r->cigarLen = 0;
+    if (res.cigar_len > 0) {
+        r->cigar = (uint32_t*)malloc((size_t)res.cigar_len * 4);
+        memcpy(r->cigar, cig.data() + res.cigar_off, (size_t)res.cigar_len * 4);
+        r->cigarLen = res.cigar_len;
+    }
+    return r;
+}
+
+extern "C" void align_destroy(s_align* a)
+{
+    if (!a) return;
+    free(a->cigar);
+    free(a);
+}
+
+extern "C" char cigar_int_to_op(uint32_t cigar_int)
+{
+    static const char ops[] = "MIDNSHP=X";
+    const uint32_t code = cigar_int & 0xfU;
+    return code < 9 ? ops[code] : 'M';
+}
+
+extern "C" uint32_t cigar_int_to_len(uint32_t cigar_int) { return cigar_int >> 4; }

@@ -1,0 +1,72 @@
+// ssw_kernels.h -- launch interfaces between the host orchestration (ssw_api.cu) and the kernels.
+#pragma once
+#include "ssw_common.cuh"
+
+namespace sswb {
+
+// ---- score passes (ssw_score.cu)
+struct ScoreArgs {
+    BatchView b;
+    Scoring sc;
+    WorkList wl;
+    unsigned char* scratch;        // per-warp scratch, (blocks * SCORE_WARPS) * scratch_stride bytes
+    long long scratch_stride;
+    long long off_col, off_bnd, off_snap;   // byte offsets of the sub-buffers inside one warp's scratch
+    int32_t rerun;                 // GOTOH forward only: 1 = deciding pass for a PS_NEED_GOTOH pair
+    int32_t* next_idx;             // TRUNC forward only: list of pairs that need the deciding GOTOH pass
+    const int32_t* next_base;      //   (same partitioning as the forward lists)
+    int32_t* next_count;
+};
+
+// bytes of scratch one warp needs for references of up to n_cap columns
+inline long long score_scratch_layout(int n_cap, long long* off_col, long long* off_bnd, long long* off_snap)
+{
+    long long o = ((long long)n_cap + 128 + 15) & ~15LL;   // ref-pair codes
+    *off_col = o; o += (long long)n_cap * 4;               // column records (colmax | H last row)
+    o = (o + 15) & ~15LL;
+    *off_bnd = o; o += (long long)n_cap * 8;               // tile boundary (H, F, colmax)
+    *off_snap = o; o += 2LL * KMAX * 32 * 4;               // best-column snapshots
+    return (o + 127) & ~127LL;
+}
+
+cudaError_t launch_score(int K, bool trunc, bool rev, const ScoreArgs& a, int blocks, cudaStream_t st);
+
+// ---- work-list construction (ssw_lists.cu)
+// list id = cls * 34 + kind * 17 + K   (cls: 0 normal / 1 long reference; kind: 0 GOTOH / 1 TRUNC; K: 1..16)
+constexpr int N_LISTS = 2 * 2 * 17;
+__host__ __device__ inline int list_id(int cls, int kind, int K) { return cls * 34 + kind * 17 + K; }
+
+struct ListSet {
+    int32_t* idx;        // n_pairs entries, partitioned by list
+    int32_t* count;      // N_LISTS
+    int32_t* base;       // N_LISTS
+    int32_t* fill;       // N_LISTS (scatter cursors)
+    int32_t* cursor;     // N_LISTS (work-fetch cursors, zeroed by build)
+};
+
+// stage 0 = forward lists from (q_len, scoring); stage 1 = reverse lists from the forward results
+cudaError_t build_lists(int stage, const BatchView& b, const Scoring& sc, int long_ref_threshold,
+                        const ListSet& ls, cudaStream_t st, int* launches);
+// all pairs that still need the CIGAR pass, in one list (count at ls.count[0])
+cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet& ls, cudaStream_t st, int* launches);
+
+// ---- banded DP + traceback (ssw_band.cu)
+struct BandArgs {
+    BatchView b;
+    Scoring sc;
+    WorkList wl;
+    unsigned char* scratch;        // per-warp direction matrix + cigar staging
+    long long scratch_stride;
+    long long dir_bytes;           // bytes of the direction matrix area inside one warp's scratch
+    int32_t cigar_stage_cap;       // ops
+    uint32_t* cigar_buf;           // device output buffer
+    long long cigar_cap;
+    unsigned long long* cigar_used;
+};
+constexpr int BAND_WARPS = 8;
+cudaError_t launch_band(const BandArgs& a, int blocks, cudaStream_t st);
+
+// ---- DPX issue-rate probe (ssw_peak.cu)
+cudaError_t dpx_peak_probe(double* lane_instr_per_s, cudaStream_t st);
+
+}  // namespace sswb

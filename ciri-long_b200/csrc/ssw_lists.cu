@@ -1,0 +1,141 @@
+// ssw_lists.cu -- device-side work lists.  Every stage of the hot path (forward pass, deciding pass,
+// reverse pass, CIGAR pass) consumes a list of pair indices grouped by the kernel instance that must
+// process them (strip height K, recurrence flavour, long-reference class), so that no stage needs a
+// host round trip: counts and cursors live in device memory and the consumers read them there.
+#include "ssw_common.cuh"
+#include "ssw_kernels.h"
+
+namespace sswb {
+
+__device__ __forceinline__ int strip_height(int m) { return m <= VSTRIPS * KMAX ? (m + VSTRIPS - 1) / VSTRIPS : KMAX; }
+
+// which list a pair belongs to in `stage`; -1 = not part of this stage
+__device__ int classify(int stage, const BatchView& b, const Scoring& sc, int long_thr, int p, int maxScore)
+{
+    PairRec* rec = b.rec + p;
+    if (stage == 0) {
+        const int m = b.q_len[p], n = b.r_len[p];
+        if (m <= 0 || n <= 0) return -1;
+        // the word flavour with gap_open == gap_extend has its own recurrence; it can only be reached when the
+        // byte flavour can overflow at all: m * max(mat) + bias >= 255
+        const int kind = (sc.go == sc.ge && (long long)m * maxScore + sc.bias >= 255) ? 1 : 0;
+        return list_id(n > long_thr ? 1 : 0, kind, strip_height(m));
+    }
+    // stage 1: reverse pass (ssw.c:834)
+    if (rec->status & (PS_PUNT | PS_UNSUPPORTED)) return -1;
+    if (sc.flag == 0 || (sc.flag == 2 && rec->score1 < sc.filters)) return -1;
+    const int m = rec->read_end1 + 1, n = rec->ref_end1 + 1;
+    if (n <= 0) return -2;          // score 0: nothing to walk (handled inline by the caller)
+    const int kind = (rec->word && sc.go == sc.ge) ? 1 : 0;
+    // the scratch class follows the full reference length (as in the forward pass), not the trimmed one
+    return list_id(b.r_len[p] > long_thr ? 1 : 0, kind, strip_height(m));
+}
+
+__device__ __forceinline__ int max_score(const Scoring& sc)
+{
+    int mx = 0;
+    for (int k = 0; k < 25; ++k) mx = sc.mat[k] > mx ? sc.mat[k] : mx;
+    return mx;
+}
+
+__global__ void list_count_kernel(int stage, BatchView b, Scoring sc, int long_thr, ListSet ls)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int maxScore = max_score(sc);
+    int id = -1;
+    if (p < b.n_pairs) {
+        id = classify(stage, b, sc, long_thr, p, maxScore);
+        PairRec* rec = b.rec + p;
+        if (stage == 0) {
+            // default record (also the answer for empty inputs)
+            rec->score1 = 0; rec->score2 = 0; rec->ref_begin1 = -1; rec->ref_end1 = -1;
+            rec->read_begin1 = -1; rec->read_end1 = -1; rec->ref_end2 = -1;
+            rec->cigar_len = 0; rec->cigar_off = 0; rec->word = 0;
+            rec->status = id < 0 ? PS_UNSUPPORTED : 0;
+        } else if (id == -2) {
+            rec->ref_begin1 = -1;                       // byte flavour, end_ref stays -1 (ssw.c:145)
+            rec->read_begin1 = rec->read_end1;
+        }
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, id >= 0);
+    if (id >= 0) {
+        const unsigned peers = __match_any_sync(act, id);
+        if ((int)(__ffs(peers) - 1) == lane_id()) atomicAdd(&ls.count[id], __popc(peers));
+    }
+}
+
+__global__ void list_scan_kernel(ListSet ls)
+{
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < N_LISTS; ++k) { ls.base[k] = run; run += ls.count[k]; ls.fill[k] = 0; ls.cursor[k] = 0; }
+    }
+}
+
+__global__ void list_scatter_kernel(int stage, BatchView b, Scoring sc, int long_thr, ListSet ls)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int maxScore = max_score(sc);
+    int id = -1;
+    if (p < b.n_pairs) id = classify(stage, b, sc, long_thr, p, maxScore);
+    const unsigned act = __ballot_sync(0xffffffffu, id >= 0);
+    if (id >= 0) {
+        const unsigned peers = __match_any_sync(act, id);
+        const int leader = __ffs(peers) - 1;
+        int pos = 0;
+        if (lane_id() == leader) pos = atomicAdd(&ls.fill[id], __popc(peers));
+        pos = __shfl_sync(peers, pos, leader);
+        ls.idx[ls.base[id] + pos + __popc(peers & ((1u << lane_id()) - 1u))] = p;
+    }
+}
+
+cudaError_t build_lists(int stage, const BatchView& b, const Scoring& sc, int long_thr, const ListSet& ls,
+                        cudaStream_t st, int* launches)
+{
+    cudaError_t e = cudaMemsetAsync(ls.count, 0, N_LISTS * sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    const int threads = 256, blocks = (b.n_pairs + threads - 1) / threads;
+    list_count_kernel<<<blocks, threads, 0, st>>>(stage, b, sc, long_thr, ls);
+    list_scan_kernel<<<1, 32, 0, st>>>(ls);
+    list_scatter_kernel<<<blocks, threads, 0, st>>>(stage, b, sc, long_thr, ls);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+// ---- CIGAR stage: one list with every pair that passes the reference's gate (ssw.c:850)
+__global__ void band_list_kernel(BatchView b, Scoring sc, ListSet ls)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false;
+    if (p < b.n_pairs) {
+        const PairRec* rec = b.rec + p;
+        const int flag = sc.flag;
+        want = !(rec->status & (PS_PUNT | PS_UNSUPPORTED)) &&
+               !(flag == 0 || (flag == 2 && rec->score1 < sc.filters)) &&
+               !((7 & flag) == 0 || ((2 & flag) != 0 && rec->score1 < sc.filters) ||
+                 ((4 & flag) != 0 && (rec->ref_end1 - rec->ref_begin1 > sc.filterd ||
+                                      rec->read_end1 - rec->read_begin1 > sc.filterd)));
+    }
+    const unsigned peers = __ballot_sync(0xffffffffu, want);
+    if (want) {
+        const int leader = __ffs(peers) - 1;
+        int pos = 0;
+        if (lane_id() == leader) pos = atomicAdd(&ls.count[0], __popc(peers));
+        pos = __shfl_sync(peers, pos, leader);
+        ls.idx[pos + __popc(peers & ((1u << lane_id()) - 1u))] = p;
+    }
+}
+
+cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet& ls, cudaStream_t st, int* launches)
+{
+    cudaError_t e = cudaMemsetAsync(ls.count, 0, N_LISTS * sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ls.cursor, 0, N_LISTS * sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    const int threads = 256, blocks = (b.n_pairs + threads - 1) / threads;
+    band_list_kernel<<<blocks, threads, 0, st>>>(b, sc, ls);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace sswb

@@ -1,0 +1,169 @@
+"""GPU parity tests: the CUDA path, called through the C ABI of libssw_cuda.so, against the CPU oracle
+(oracle/ssw_oracle.c) and the golden vectors generated from the unmodified reference.  Bit-exact on
+every field: score, ref/read begin/end, score2, ref_end2, CIGAR ops."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sw():
+    from ciri_long_b200 import ssw_wrap
+    assert ssw_wrap.Aligner.libssw.ssw_cuda_device_count() > 0, "no CUDA device: the product has no CPU path"
+    return ssw_wrap
+
+
+def run_batch(sw, b, flag=1):
+    with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, b.match, b.mismatch, b.gap_open,
+                        b.gap_extend, flag=flag) as d:
+        d.run()
+        return d.fetch()
+
+
+def check_batch(sw, oracle, b, flag=1, sample=None):
+    rec, cig = run_batch(sw, b, flag)
+    mat = O.make_mat(b.match, b.mismatch)
+    idx = range(len(b)) if sample is None else sample
+    bad = []
+    for i in idx:
+        exp = oracle.align(b.query(i), b.ref(i), mat, b.gap_open, b.gap_extend, flag=flag)
+        r = rec[i]
+        got = dict(score=int(r["score1"]), score2=int(r["score2"]), ref_begin=int(r["ref_begin1"]),
+                   ref_end=int(r["ref_end1"]), read_begin=int(r["read_begin1"]), read_end=int(r["read_end1"]),
+                   ref_end2=int(r["ref_end2"]),
+                   cigar=cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]].tolist())
+        if r["status"] != 0 or not O.same(got, exp) or int(r["word"]) != exp["word"]:
+            bad.append((i, int(r["status"]), int(r["word"]), {k: got[k] for k in O.FIELDS},
+                        {k: exp[k] for k in O.FIELDS}, exp["word"], got["cigar"] == exp["cigar"]))
+    assert not bad, "%s: %d mismatches, first: %s" % (b.name, len(bad), bad[:3])
+    return rec, cig
+
+
+def test_golden_cases(sw, golden):
+    """every committed golden vector (fuzz, overflow boundary, planted repeats, G5-G7) per parameter set"""
+    from ciri_long_b200 import workloads as W
+    by_params = {}
+    for c in golden["cases"]:
+        by_params.setdefault(tuple(c["params"]), []).append(c)
+    for p, cases in by_params.items():
+        b = W.from_lists([O.encode(c["query"]) for c in cases], [O.encode(c["ref"]) for c in cases], p)
+        rec, cig = run_batch(sw, b)
+        for i, c in enumerate(cases):
+            e, r = c["expected"], rec[i]
+            got = (int(r["score1"]), int(r["score2"]), int(r["ref_begin1"]), int(r["ref_end1"]),
+                   int(r["read_begin1"]), int(r["read_end1"]), int(r["ref_end2"]))
+            want = tuple(e[k] for k in O.FIELDS)
+            assert r["status"] == 0, (c["name"], int(r["status"]))
+            assert got == want, (c["name"], got, want)
+            assert cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]].tolist() == e["cigar"], c["name"]
+
+
+def test_golden_testfa(sw, golden):
+    """tests/test.fa of the reference: 437 nt vs 430,314 nt, both orientations, both parameter sets"""
+    from ciri_long_b200 import workloads as W
+    for c in golden["testfa"]:
+        b = W.from_lists([golden["seqs"][c["query"]]], [golden["seqs"][c["ref"]]], tuple(c["params"]))
+        rec, cig = run_batch(sw, b)
+        e, r = c["expected"], rec[0]
+        got = (int(r["score1"]), int(r["score2"]), int(r["ref_begin1"]), int(r["ref_end1"]),
+               int(r["read_begin1"]), int(r["read_end1"]), int(r["ref_end2"]))
+        assert r["status"] == 0, (c["name"], int(r["status"]))
+        assert got == tuple(e[k] for k in O.FIELDS), (c["name"], got)
+        assert cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]].tolist() == e["cigar"], c["name"]
+
+
+@pytest.mark.parametrize("params", [(1, 1, 1, 1), (10, 4, 8, 2), (2, 2, 3, 1), (2, 2, 2, 2)])
+def test_bsj_refinement_shape(sw, oracle, params):
+    from ciri_long_b200 import workloads as W
+    check_batch(sw, oracle, W.bsj_refinement_pairs(96, seed=11, params=params))
+
+
+def test_rolling_circle_shape(sw, oracle):
+    from ciri_long_b200 import workloads as W
+    check_batch(sw, oracle, W.rolling_circle_pairs(24, seed=12, read_min=800, read_max=3000))
+
+
+@pytest.mark.parametrize("length", [64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("params", [(1, 1, 1, 1), (10, 4, 8, 2)])
+def test_square_sweep(sw, oracle, length, params):
+    from ciri_long_b200 import workloads as W
+    n = max(4, 2048 // length)
+    check_batch(sw, oracle, W.square_pairs(n, length, params=params))
+    check_batch(sw, oracle, W.square_pairs(n, length, params=params), flag=0)
+
+
+def test_tiny_junction_pairs(sw, oracle):
+    from ciri_long_b200 import workloads as W
+    check_batch(sw, oracle, W.junction_pairs(2000, seed=13))
+
+
+def test_overflow_boundary(sw, oracle):
+    from ciri_long_b200 import workloads as W
+    check_batch(sw, oracle, W.overflow_boundary_pairs())
+    check_batch(sw, oracle, W.overflow_boundary_pairs(params=(2, 2, 2, 2), lengths=range(118, 134)))
+    check_batch(sw, oracle, W.overflow_boundary_pairs(params=(10, 4, 8, 2), lengths=range(20, 30)))
+
+
+def test_ragged_and_degenerate(sw, oracle):
+    """1-base sequences, all-N, no match at all, query longer than reference"""
+    from ciri_long_b200 import workloads as W
+    qs = [np.array([0], np.int8), np.array([4, 4, 4, 4], np.int8), np.zeros(24, np.int8) + 1,
+          np.arange(200, dtype=np.int8) % 4, np.array([2, 3], np.int8)]
+    rs = [np.array([0], np.int8), np.array([0, 1, 2, 3], np.int8), np.zeros(20, np.int8),
+          np.arange(37, dtype=np.int8) % 4, np.arange(3000, dtype=np.int8) % 4]
+    for p in [(1, 1, 1, 1), (10, 4, 8, 2)]:
+        check_batch(sw, oracle, W.from_lists(qs, rs, p, name="degenerate"))
+
+
+def test_large_batch_properties(sw, oracle):
+    """BASELINE-sized shape at reduced count: sampled oracle parity + size-independent invariants"""
+    from ciri_long_b200 import workloads as W
+    b = W.bsj_refinement_pairs(20000, seed=21)
+    rec, cig = check_batch(sw, oracle, b, sample=range(0, 20000, 400))
+    assert (rec["status"] == 0).all()
+    # CIGAR consistency: M+I covers the aligned query span, M+D the reference span (1/1/1/1: no dropped deletions)
+    ops = cig & 0xF
+    lens = (cig >> 4).astype(np.int64)
+    seg = np.repeat(np.arange(len(b)), rec["cigar_len"])
+    order = np.argsort(rec["cigar_off"], kind="stable")
+    assert (np.diff(rec["cigar_off"][order]) == rec["cigar_len"][order][:-1]).all()      # dense, no overlap
+    seg = np.repeat(order, rec["cigar_len"][order])
+    qspan = np.bincount(seg, weights=np.where(ops != 2, lens, 0), minlength=len(b))
+    rspan = np.bincount(seg, weights=np.where(ops != 1, lens, 0), minlength=len(b))
+    assert (qspan == rec["read_end1"] - rec["read_begin1"] + 1).all()
+    assert (rspan == rec["ref_end1"] - rec["ref_begin1"] + 1).all()
+    # running the same resident batch twice gives identical results (idempotence of ssw_batch_run)
+    with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, 1, 1, 1, 1) as d:
+        d.run(); r1, c1 = d.fetch()
+        d.run(); r2, c2 = d.fetch()
+    for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len"):
+        assert (r1[k] == r2[k]).all() and (r1[k] == rec[k]).all()
+
+
+def test_wrapper_drop_in(sw, golden):
+    """Aligner.align / align_batch / align_pairs mirror the reference wrapper (incl. soft-clipped CIGAR string)"""
+    cases = golden["cases"][:40]
+    for c in cases[:8]:
+        p = c["params"]
+        al = sw.Aligner(c["ref"], match=p[0], mismatch=p[1], gap_open=p[2], gap_extend=p[3],
+                        report_secondary=True, report_cigar=True)
+        res = al.align(c["query"])
+        e = c["expected"]
+        assert (res.score, res.ref_begin, res.ref_end, res.query_begin, res.query_end) == \
+            (e["score"], e["ref_begin"], e["ref_end"], e["read_begin"], e["read_end"])
+        assert (res.score2 or 0) == e["score2"] and res.cigar_string == e["cigar_string"]
+        assert al.align(c["query"], min_score=10 ** 6) is None
+    p = tuple(cases[0]["params"])
+    same = [c for c in cases if tuple(c["params"]) == p]
+    out = sw.align_pairs([c["ref"] for c in same], [c["query"] for c in same], *p, report_secondary=True,
+                         report_cigar=True)
+    for c, res in zip(same, out):
+        assert res.cigar_string == c["expected"]["cigar_string"] and res.score == c["expected"]["score"]
+    al = sw.Aligner(same[0]["ref"], *p, report_cigar=False)
+    out = al.align_batch([c["query"] for c in same])
+    ref0 = [sw.Aligner(same[0]["ref"], *p).align(c["query"]) for c in same[:5]]
+    for a, b_ in zip(out[:5], ref0):
+        assert (a.score, a.ref_begin, a.query_end) == (b_.score, b_.ref_begin, b_.query_end) and a.cigar_string is None
