@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- batched SSW GCUPS (score + coords + CIGAR) on B200 vs host libssw.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+
+A "step" is one pass of the whole hot path (forward score pass, deciding byte-flavour pass, reverse
+pass, CIGAR pass) over one batch of synthetic pairs.  Workload = BASELINE.json configs[1]: BSJ-refinement
+pairs, 300-800 nt consensus segment (ONT-like noise, 1 % N) vs a 2 kb genomic flank, find_bsj scoring
+1/1/1/1, 1,048,576 pairs per GPU (weak scaling: every rank owns its own batch, no collective on the data
+path).  GCUPS = sum(len(query) * len(ref)) / seconds / 1e9 -- forward-matrix cells only, the reverse pass,
+the 16-bit re-run and the banded CIGAR DP are not counted as extra cells.
+
+  value     inputs resident in HBM, K x ssw_batch_run timed with CUDA events on the launching stream
+  e2e       the public call (DeviceBatch create + run + fetch) from pinned HOST buffers, H2D and D2H inside
+  roofline  forward score-pass kernels only: achieved GCUPS vs the DPX peak (VIADDMNMX.S16x2 issue rate
+            measured live by ssw_cuda_dpx_peak / 3 lane-instructions per cell)
+  cpu_baseline / --impl reference: the unmodified reference libssw.so (oracle/_ref, built from
+            /root/reference by oracle/Makefile) in a multiprocessing pool over all host cores, chunks of
+            250 pairs like find_bsj.py:338-345, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIRS_PER_GPU = 1 << 20
+CPU_SAMPLE_PAIRS = 32768
+PARAMS = (1, 1, 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: reference libssw.so (or the oracle port) over all host cores
+
+_W = {}
+
+
+def _cpu_worker_init(kind):
+    from oracle import oracle as O
+    _W["lib"] = O.RefLib() if kind == "reference" else O.Oracle()
+    _W["mat"] = O.make_mat(PARAMS[0], PARAMS[1])
+
+
+def _cpu_worker(chunk):
+    b = _W["batch"]
+    lib, mat = _W["lib"], _W["mat"]
+    out = []
+    for i in chunk:
+        r = lib.align(b.query(i), b.ref(i), mat, PARAMS[2], PARAMS[3])
+        out.append((r["score"], r["ref_begin"], r["ref_end"], r["read_begin"], r["read_end"], len(r["cigar"])))
+    return out
+
+
+def cpu_run(batch, cores, kind):
+    """Align every pair of `batch` on `cores` processes; returns (seconds, results)."""
+    import multiprocessing as mp
+    _W["batch"] = batch                     # inherited by fork, nothing is pickled
+    chunks = [range(i, min(i + 250, len(batch))) for i in range(0, len(batch), 250)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(kind,)) as pool:
+        pool.map(_cpu_worker, chunks[:cores])          # warm the workers (library load, page-in)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, chunks)
+        dt = time.perf_counter() - t0
+    return dt, [x for c in res for x in c]
+
+
+def cpu_kind():
+    from oracle import oracle as O
+    O.build(ref=True)
+    return "reference" if O.RefLib.available() else "port"
+
+
+def cpu_baseline(sample_pairs):
+    from ciri_long_b200 import workloads as W
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    batch = W.bsj_refinement_pairs(sample_pairs, seed=W.SEED_BASE + 2)
+    dt, _ = cpu_run(batch, cores, kind)
+    return dict(value=batch.cells / dt / 1e9, unit="GCUPS", cores=cores, kind=kind,
+                sample="%d pairs of the same workload (C2 recipe, numpy seed %d), %s via ctypes on pre-encoded "
+                       "int8 arrays, Pool(%d) x chunks of 250, flag=1 (score+coords+CIGAR), %.1f s"
+                       % (sample_pairs, W.SEED_BASE + 2,
+                          "unmodified reference libssw.so (oracle/_ref)" if kind == "reference" else "oracle port",
+                          cores, dt)), batch
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k] == "Active" for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from ciri_long_b200 import workloads as W
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    batch = W.bsj_refinement_pairs(args.cpu_sample, seed=W.SEED_BASE + 2)
+    times = []
+    for s in range(args.warmup + args.steps):
+        dt, _ = cpu_run(batch, cores, kind)
+        if s >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = batch.cells / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": "batched SSW GCUPS (score+coords+CIGAR)", "value": val, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 (SSE2)",
+        "data": "synthetic", "config": {"workload": "C2 BSJ-refinement pairs: 300-800 nt vs 2 kb, params 1/1/1/1, flag=1",
+                                        "pairs_per_step": len(batch)},
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": kind,
+                         "sample": "%d pairs per step, Pool(%d) x chunks of 250, ctypes on pre-encoded int8" % (len(batch), cores)},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank, world, local_rank):
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_baseline(args.cpu_sample)          # before CUDA is initialised in this process (fork)
+
+    import torch
+    import ciri_long_b200  # noqa: F401
+    from ciri_long_b200 import ssw_wrap as sw, workloads as W
+    from oracle import oracle as O
+
+    if not torch.cuda.is_available() or sw.Aligner.libssw.ssw_cuda_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = W.bsj_refinement_pairs_torch(args.pairs, dev, seed=W.SEED_BASE + 2 + 1000 * rank, params=PARAMS)
+    cells = batch.cells
+    # pinned host staging of the inputs (the e2e path copies from here every step)
+    pinned = {}
+    for k in ("seqs", "q_off", "q_len", "r_off", "r_len"):
+        t = torch.from_numpy(getattr(batch, k)).pin_memory()
+        pinned[k] = t
+        setattr(batch, k, t.numpy())
+    stream = torch.cuda.Stream(device=dev)       # the library enqueues on this stream; events are recorded on it
+    torch.cuda.set_stream(stream)
+
+    # ---- device-resident throughput
+    d = sw.DeviceBatch(batch.seqs, batch.q_off, batch.q_len, batch.r_off, batch.r_len, *PARAMS, flag=1,
+                       device=local_rank, stream=stream.cuda_stream)
+    for _ in range(args.warmup):
+        d.run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        d.run()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    stage = d.stage_ms()
+    launches = d.launch_count()
+    rec, cig = d.fetch()
+    d.close()
+
+    # ---- parity spot check against the CPU checker (not timed)
+    checker = O.RefLib() if O.RefLib.available() else O.Oracle()
+    mat = O.make_mat(PARAMS[0], PARAMS[1])
+    n_chk = 0
+    for i in range(0, len(batch), max(1, len(batch) // 64)):
+        e = checker.align(batch.query(i), batch.ref(i), mat, PARAMS[2], PARAMS[3])
+        r = rec[i]
+        got = dict(score=int(r["score1"]), score2=int(r["score2"]), ref_begin=int(r["ref_begin1"]),
+                   ref_end=int(r["ref_end1"]), read_begin=int(r["read_begin1"]), read_end=int(r["read_end1"]),
+                   ref_end2=int(r["ref_end2"]), cigar=cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]].tolist())
+        if (r["status"] & 0xff) != 0 or not O.same(got, e):
+            raise SystemExit("bench.py: parity check failed on pair %d: %r vs %r" % (i, got, e))
+        n_chk += 1
+    n_bad_status = int(((rec["status"] & 0xff) != 0).sum())
+
+    # ---- end to end through the public call, host buffers in, host results out
+    def e2e_step():
+        with sw.DeviceBatch(batch.seqs, batch.q_off, batch.q_len, batch.r_off, batch.r_len, *PARAMS, flag=1,
+                            device=local_rank, stream=stream.cuda_stream) as b:
+            b.run()
+            r, c = b.fetch()
+            return b.h2d_bytes, b.d2h_bytes
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        h2d, d2h = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+
+    peak_lane, _ = sw.dpx_peak(local_rank)
+
+    # ---- max over ranks, whole-job aggregate
+    ms_step = ms_total / args.steps
+    vals = torch.tensor([ms_step, e2e_s, float(cells), float(stage[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_step, e2e_s = float(mx[0]), float(mx[1])
+        cells_all = float(sm[2])
+    else:
+        cells_all = float(cells)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    fwd_ms = float(stage[0])
+    fwd_gcups = cells / (fwd_ms * 1e-3) / 1e9
+    peak_gcups = peak_lane / 3.0 / 1e9
+    hbm_bytes = float(batch.seqs.nbytes + 24 * len(batch) + rec.nbytes + 4 * len(cig))
+    out = {
+        "metric": "batched SSW GCUPS (score+coords+CIGAR)",
+        "value": cells_all / (ms_step * 1e-3) / 1e9,
+        "unit": "GCUPS",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "s16x2 (DPX), int32 in the CIGAR pass", "data": "synthetic",
+        "config": {"workload": "C2 BSJ-refinement pairs: 300-800 nt consensus segment (5/4/4 % sub/ins/del, 1 % N) "
+                               "vs 2 kb genomic flank, find_bsj params 1/1/1/1, flag=1 (score+coords+CIGAR)",
+                   "pairs_per_gpu": len(batch), "cells_per_gpu": cells,
+                   "l2": "inputs (%.2f GB per GPU) are larger than L2" % (batch.seqs.nbytes / 1e9),
+                   "parity": "%d sampled pairs bit-exact vs %s; %d pairs with non-OK status"
+                             % (n_chk, "reference libssw.so" if O.RefLib.available() else "oracle port", n_bad_status)},
+        "stage_ms": {"forward": fwd_ms, "deciding": float(stage[1]), "reverse": float(stage[2]), "cigar": float(stage[3])},
+        "roofline": {"bound": "dpx", "achieved": fwd_gcups, "peak": peak_gcups, "unit": "GCUPS",
+                     "frac": fwd_gcups / peak_gcups, "traffic": None,
+                     "kernel": "score_kernel<K,TRUNC,fwd> (forward score pass, all strip heights)",
+                     "peak_source": "ssw_cuda_dpx_peak: %.3e VIADDMNMX.S16x2 lane-instr/s measured in this run / 3 per cell" % peak_lane,
+                     "whole_step_frac": cells / (ms_step * 1e-3) / 1e9 / peak_gcups if world == 1 else None,
+                     "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                             "note": "algorithmic bytes per step / step time; the path is DPX-bound, not HBM-bound"}},
+        "e2e": {"value": cells_all / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+        "gpu_launches": int(launches) * args.steps,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE_PAIRS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

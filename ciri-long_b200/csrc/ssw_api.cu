@@ -66,6 +66,7 @@ struct ssw_batch {
     bool have[2][2][KMAX + 1];           // forward lists known to be non-empty: [cls][kind][K]
     int64_t launches = 0;
     std::vector<PairRec> h_rec;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last run
 
     BatchView view() const { return BatchView{d_seqs, d_qoff, d_qlen, d_roff, d_rlen, d_mask, d_rec, n}; }
     ListSet lists() const { return ListSet{d_idx, d_meta, d_meta + N_LISTS, d_meta + 2 * N_LISTS, d_meta + 3 * N_LISTS}; }
@@ -99,6 +100,7 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     cudaFree(b->d_seqs); cudaFree(b->d_qoff); cudaFree(b->d_roff); cudaFree(b->d_qlen); cudaFree(b->d_rlen);
     cudaFree(b->d_mask); cudaFree(b->d_rec); cudaFree(b->d_idx); cudaFree(b->d_idx2); cudaFree(b->d_meta);
     cudaFree(b->d_sscr[0]); cudaFree(b->d_sscr[1]); cudaFree(b->d_bscr); cudaFree(b->d_cigar); cudaFree(b->d_cigar_used);
+    for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -167,7 +169,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->bstage = b->max_q + b->max_r + 16;
         b->bdir = std::min<long long>(std::max<long long>(65536, 192LL * std::min(b->max_q, b->max_r + b->max_q)), 16LL << 20);
         b->bstride = ((long long)b->bstage * 4 + b->bdir + 255) & ~255LL;
-        long long blocks = std::min<long long>((long long)b->sms * 2, (n + BAND_WARPS - 1) / BAND_WARPS);
+        long long blocks = std::min<long long>((long long)b->sms * 4, (n + BAND_WARPS - 1) / BAND_WARPS);
         blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->bstride * BAND_WARPS)));
         b->bblocks = (int)blocks;
         CU_TRY(cudaMalloc(&b->d_bscr, (size_t)(blocks * BAND_WARPS * b->bstride)));
@@ -211,6 +213,8 @@ extern "C" ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs
         b->own_stream = true;
     }
     if (batch_alloc(b, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len) != SSW_OK) { ssw_batch_destroy(b); return nullptr; }
+    for (int k = 0; k < 5; ++k)
+        if (cudaEventCreate(&b->ev[k]) != cudaSuccess) { set_error("cudaEventCreate"); ssw_batch_destroy(b); return nullptr; }
     return b;
 }
 
@@ -236,6 +240,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
     };
 
     // ---- forward pass
+    CU_TRY(cudaEventRecord(b->ev[0], st));
     CU_TRY(build_lists(0, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
     for (int cls = 0; cls < 2; ++cls)
         for (int kind = 0; kind < 2; ++kind)
@@ -248,6 +253,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                 CU_TRY(launch_score(K, kind == 1, false, a, b->sblocks[cls], st));
                 ++launches;
             }
+    CU_TRY(cudaEventRecord(b->ev[1], st));
     // ---- deciding byte-flavour pass for pairs whose truncated-F pass stayed below the 8-bit limit
     for (int cls = 0; cls < 2; ++cls)
         for (int K = 1; K <= KMAX; ++K) {
@@ -259,6 +265,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
             CU_TRY(launch_score(K, false, false, a, b->sblocks[cls], st));
             ++launches;
         }
+    CU_TRY(cudaEventRecord(b->ev[2], st));
     if (b->sc.flag != 0) {
         // ---- reverse pass: strip height follows the read prefix, so any K up to the forward maximum can occur
         CU_TRY(build_lists(1, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
@@ -275,6 +282,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                 }
             }
         }
+        CU_TRY(cudaEventRecord(b->ev[3], st));
         // ---- CIGAR pass
         CU_TRY(build_band_list(view, b->sc, ls, st, &launches));
         BandArgs ba;
@@ -283,10 +291,27 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         ba.scratch = b->d_bscr; ba.scratch_stride = b->bstride; ba.dir_bytes = b->bdir;
         ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap;
         ba.cigar_used = b->d_cigar_used;
-        CU_TRY(launch_band(ba, b->bblocks, st));
-        ++launches;
+        ba.next_idx = b->d_idx2; ba.next_count = b->count2(); 
+        CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
+        CU_TRY(launch_band(false, ba, b->bblocks, st));
+        ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+        CU_TRY(launch_band(true, ba, b->bblocks, st));
+        launches += 2;
     }
+    else CU_TRY(cudaEventRecord(b->ev[3], st));
+    CU_TRY(cudaEventRecord(b->ev[4], st));
     b->launches = launches;
+    return SSW_OK;
+}
+
+// Device time of the four stages of the last ssw_batch_run, in ms: forward score pass, deciding
+// byte-flavour pass, reverse pass, CIGAR pass (CUDA events on the batch's stream; waits for the run).
+extern "C" int ssw_batch_stage_ms(ssw_batch* b, float* ms4)
+{
+    if (!b || !ms4) return SSW_ERR_ARG;
+    CU_TRY(cudaSetDevice(b->device));
+    CU_TRY(cudaEventSynchronize(b->ev[4]));
+    for (int k = 0; k < 4; ++k) CU_TRY(cudaEventElapsedTime(&ms4[k], b->ev[k], b->ev[k + 1]));
     return SSW_OK;
 }
 
@@ -323,8 +348,12 @@ static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
     ba.wl = WorkList{ls.idx, nullptr, ls.count, ls.cursor};
     ba.scratch = scr; ba.scratch_stride = stride; ba.dir_bytes = need;
     ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap; ba.cigar_used = b->d_cigar_used;
-    CU_TRY(launch_band(ba, blocks, st));
-    b->launches += 1;
+    ba.next_idx = b->d_idx2; ba.next_count = b->count2();
+    CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
+    CU_TRY(launch_band(false, ba, blocks, st));
+    ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+    CU_TRY(launch_band(true, ba, blocks, st));
+    b->launches += 2;
     for (int32_t p : big)
         CU_TRY(cudaMemcpyAsync(&b->h_rec[p], &b->d_rec[p], sizeof(PairRec), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));

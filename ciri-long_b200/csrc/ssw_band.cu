@@ -1,17 +1,25 @@
 // ssw_band.cu -- banded affine DP + traceback -> CIGAR on the trimmed rectangle.
 //
 // Replaces banded_sw (reference ssw.c:548-735) as called from ssw_align (ssw.c:852-856).  The
-// reference fills the band cell by cell in scalar int32 code; here one warp owns a pair and computes a
-// whole band row at a time:
-//   * cells are addressed by their band diagonal kk = j - i + w, so the vertical neighbour of slot kk is
-//     slot kk+1 of the previous row and the diagonal neighbour is slot kk itself: the row buffers are
-//     updated in place;
-//   * the horizontal-gap chain F (a serial dependency along the row) is an exclusive max-plus prefix
-//     scan over the lanes (valid because gap_open >= gap_extend on this path);
-//   * one direction byte per cell (vertical source, horizontal source, H source) goes to a per-warp
-//     scratch matrix; the band doubles while max < score1 exactly like ssw.c:631-632;
-//   * lane 0 walks the matrix back from the bottom-right corner with the reference's state machine
-//     (ssw.c:642-696), run-length encodes, and the warp writes the reversed ops to the output buffer.
+// reference fills the band cell by cell in scalar int32 code; here one warp owns a pair:
+//
+//   * cells are addressed by their band diagonal kk = j - i + w (w = band half-width): the vertical
+//     neighbour of (i, kk) is (i-1, kk+1), the diagonal neighbour is (i-1, kk), the horizontal one is
+//     (i, kk-1);
+//   * lane l owns a block of DPL = 2P consecutive diagonals and keeps H and the vertical-gap score E of
+//     the previous row of those diagonals in registers.  Lanes run a skewed wavefront: in iteration r
+//     lane l computes row r - l, left to right inside its block, so the horizontal-gap chain F is a plain
+//     register chain, the left neighbour of the block comes from lane l-1 (one iteration old) and the
+//     vertical neighbour of the block's last diagonal from lane l+1 (this iteration): two shuffles of
+//     (H, gap) per row instead of a scan;
+//   * one direction byte per cell (vertical source, horizontal source, H source), written as one
+//     aligned DPL-byte store per lane and row into a per-warp scratch matrix with a padded row stride;
+//     the band doubles while max < score1 exactly like ssw.c:631-632;
+//   * the traceback (ssw.c:642-696) walks the matrix through a shared-memory window that the warp
+//     refills 4 KB at a time; lane 0 runs the reference's state machine, run-length encodes, and the warp
+//     writes the reversed ops to the output buffer.
+// Bands wider than 1024 diagonals (never seen on the benchmark shapes) use a row-parallel variant in
+// which F is an exclusive max-plus prefix scan over the lanes.
 // Tie rules, the "stop at read row 0" rule and the zeroed vertical neighbour of the last column in the
 // first w+1 rows (ssw.c:595-596) are reproduced; see oracle/ssw_oracle.c:orc_band_cigar.
 #include "ssw_common.cuh"
@@ -20,23 +28,203 @@
 namespace sswb {
 
 constexpr int NEG_INF = -(1 << 29);
+constexpr int TB_WINDOW = 4096;          // bytes of shared memory per warp for the traceback window
 
 // direction byte: bit0 vertical gap opened (code 3) / extended (2); bit1 horizontal gap opened (5) /
 // extended (4); bits 2-3 H source: 0 diagonal, 1 vertical gap, 2 horizontal gap
 __device__ __forceinline__ uint32_t cigar_pack(uint32_t len, int op) { return (len << 4) | (uint32_t)op; }
 
-__device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws)
+struct BandJob {
+    const int8_t* ref;      // trimmed rectangle
+    const int8_t* read;
+    int refLen, readLen, bw;
+    int go, ge;
+    const int8_t* mat;      // 5x5 in constant bank
+};
+
+// ---- wavefront variant: 32 lanes x DPL diagonals, one row per lane and iteration -------------------
+template <int P>
+__device__ __forceinline__ int band_fill_wave(const BandJob& jb, unsigned char* dir, int rowStride, int maxv)
+{
+    constexpr int DPL = 2 * P;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = lane_id();
+    const int bw = jb.bw, go = jb.go, ge = jb.ge, refLen = jb.refLen, readLen = jb.readLen;
+    const int kkBase = lane * DPL;
+    int Hp[DPL], Ep[DPL], rc[DPL];
+    {
+        const int i0 = -lane;                                   // row of iteration 0
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+            Hp[d] = 0; Ep[d] = 0;
+            const int j = i0 + kkBase + d - bw;
+            int c = 4;
+            if (j >= 0 && j < refLen) { c = jb.ref[j]; if ((unsigned)c > 4u) c = 4; }
+            rc[d] = c;
+        }
+    }
+    int lastH = 0, lastF = 0;                                   // H, F of my last diagonal in the row I just finished
+    const int iters = readLen + 31;
+    for (int r = 0; r < iters; ++r) {
+        const int i = r - lane;
+        const bool rowOk = i >= 0 && i < readLen;
+        // left neighbour of my block: lane-1's last cell of the same row (computed one iteration ago)
+        int Hl = __shfl_up_sync(FULL, lastH, 1), Fl = __shfl_up_sync(FULL, lastF, 1);
+        if (lane == 0) { Hl = 0; Fl = 0; }
+        int rd = 4;
+        if (rowOk) { rd = jb.read[i]; if ((unsigned)rd > 4u) rd = 4; }
+        const bool quirk = i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;   // ssw.c:595-596
+        unsigned dirw[(DPL + 3) / 4];
+#pragma unroll
+        for (int w = 0; w < (DPL + 3) / 4; ++w) dirw[w] = 0;
+        int upH = 0, upE = 0;                                   // (i-1, first diagonal of lane+1), known after d == 0
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) {
+            const int kk = kkBase + d;
+            const int j = i + kk - bw;
+            const bool valid = rowOk && kk <= 2 * bw && j >= 0 && j < refLen;
+            int Hu, Eu;
+            if (d + 1 < DPL) { Hu = Hp[d + 1]; Eu = Ep[d + 1]; }
+            else { Hu = upH; Eu = upE; }
+            if (quirk && j == refLen - 1) { Hu = 0; Eu = 0; }
+            const int s = jb.mat[rc[d] * 5 + rd];
+            const int eopen = Hu - go, eext = Eu - ge;
+            const int E = eopen > eext ? eopen : eext;
+            const int de = eopen > eext ? 1 : 0;
+            const int fopen = Hl - go, fext = Fl - ge;
+            const int F = fopen > fext ? fopen : fext;
+            const int df = fopen > fext ? 2 : 0;
+            const int e1 = E > 0 ? E : 0, f1 = F > 0 ? F : 0;
+            const int gapbest = e1 > f1 ? e1 : f1;
+            const int dg = Hp[d] + s;
+            int H = gapbest > dg ? gapbest : dg;
+            int dh = 0;
+            if (gapbest > dg) dh = e1 > f1 ? 4 : 8;
+            int Eo = E, Fo = F;
+            if (!valid) { H = 0; Eo = 0; Fo = 0; }
+            else if (H > maxv) maxv = H;
+            dirw[d >> 2] |= (unsigned)(de | df | dh) << (8 * (d & 3));
+            Hp[d] = H; Ep[d] = Eo;
+            Hl = H; Fl = Fo;
+            if (d == 0) {
+                // vertical neighbour of my last diagonal: lane+1's first cell of row i-1, which lane+1
+                // has just computed in this iteration
+                upH = __shfl_down_sync(FULL, H, 1);
+                upE = __shfl_down_sync(FULL, Eo, 1);
+                if (lane == 31) { upH = 0; upE = 0; }
+            }
+        }
+        lastH = Hl; lastF = Fl;
+        if (rowOk) {
+            unsigned char* p = dir + (size_t)i * rowStride + kkBase;
+            if (DPL == 2) *reinterpret_cast<unsigned short*>(p) = (unsigned short)dirw[0];
+            else if (DPL == 4) *reinterpret_cast<unsigned*>(p) = dirw[0];
+            else if (DPL == 8) *reinterpret_cast<uint2*>(p) = make_uint2(dirw[0], dirw[1]);
+            else {
+#pragma unroll
+                for (int w = 0; w < DPL / 16; ++w)
+                    reinterpret_cast<uint4*>(p)[w] = make_uint4(dirw[4 * w], dirw[4 * w + 1], dirw[4 * w + 2], dirw[4 * w + 3]);
+            }
+        }
+        // next row: every diagonal moves one reference base to the right
+#pragma unroll
+        for (int d = 0; d + 1 < DPL; ++d) rc[d] = rc[d + 1];
+        {
+            const int j = i + 1 + kkBase + DPL - 1 - bw;
+            int c = 4;
+            if (j >= 0 && j < refLen) { c = jb.ref[j]; if ((unsigned)c > 4u) c = 4; }
+            rc[DPL - 1] = c;
+        }
+    }
+    return __reduce_max_sync(FULL, maxv);
+}
+
+// ---- row-parallel variant for very wide bands: F by max-plus prefix scan ---------------------------
+__device__ int band_fill_scan(const BandJob& jb, int* Hrow, unsigned char* dir, int rowStride, int maxv)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = lane_id();
+    const int bw = jb.bw, go = jb.go, ge = jb.ge, refLen = jb.refLen, readLen = jb.readLen;
+    int* Erow = Hrow + (2 * bw + 4);
+    for (int k = lane; k < 2 * bw + 4; k += 32) { Hrow[k] = 0; Erow[k] = 0; }
+    __syncwarp();
+    for (int i = 0; i < readLen; ++i) {
+        const int beg = i - bw > 0 ? i - bw : 0;
+        const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
+        if (beg > end) break;
+        const int W = end - beg + 1;
+        const int kk0 = beg - i + bw;
+        int rd = jb.read[i]; if ((unsigned)rd > 4u) rd = 4;
+        const bool quirk = i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;
+        unsigned char* drow = dir + (size_t)i * rowStride;
+        int carryV = NEG_INF, carryH = 0, carryF = 0;
+        for (int t0 = 0; t0 < W; t0 += 32) {
+            const int t = t0 + lane;
+            const bool act = t < W;
+            const int kk = kk0 + t;
+            const int j = beg + t;
+            int Hd = 0, Hu = 0, Eu = 0, s = 0;
+            if (act) {
+                Hd = Hrow[kk]; Hu = Hrow[kk + 1]; Eu = Erow[kk + 1];
+                if (quirk && j == refLen - 1) { Hu = 0; Eu = 0; }
+                int rf = jb.ref[j]; if ((unsigned)rf > 4u) rf = 4;
+                s = jb.mat[rf * 5 + rd];
+            }
+            __syncwarp();
+            const int eopen = Hu - go, eext = Eu - ge;
+            const int E = eopen > eext ? eopen : eext;
+            const int de = eopen > eext ? 1 : 0;
+            const int e1 = E > 0 ? E : 0;
+            const int dg = Hd + s;
+            const int A = e1 > dg ? e1 : dg;
+            int inc = act ? A + t * ge : NEG_INF;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d && o > inc) inc = o;
+            }
+            int exc = __shfl_up_sync(FULL, inc, 1);
+            if (lane == 0) exc = NEG_INF;
+            if (carryV > exc) exc = carryV;
+            int F = -ge * (t + 1);
+            if (exc > NEG_INF) { const int f2 = exc - go - (t - 1) * ge; if (f2 > F) F = f2; }
+            const int H = A > F ? A : F;
+            int Hl = __shfl_up_sync(FULL, H, 1), Fl = __shfl_up_sync(FULL, F, 1);
+            if (lane == 0) { Hl = carryH; Fl = carryF; }
+            const int df = (Hl - go > Fl - ge) ? 2 : 0;
+            const int f1 = F > 0 ? F : 0;
+            const int gapbest = e1 > f1 ? e1 : f1;
+            int dh = 0;
+            if (gapbest > dg) dh = e1 > f1 ? 4 : 8;
+            if (act) {
+                Hrow[kk] = H; Erow[kk] = E;
+                drow[kk] = (unsigned char)(de | df | dh);
+                if (H > maxv) maxv = H;
+            }
+            const int top = __shfl_sync(FULL, inc, 31);
+            carryV = top > carryV ? top : carryV;
+            carryH = __shfl_sync(FULL, H, 31);
+            carryF = __shfl_sync(FULL, F, 31);
+            __syncwarp();
+        }
+    }
+    return __reduce_max_sync(FULL, maxv);
+}
+
+// WIDE = false: bands of up to 128 diagonals (the common case, few registers); a pair whose band grows
+// past that is handed to the WIDE instance (its own launch) together with the band width reached and the
+// running maximum, which is all the doubling loop carries from one width to the next (ssw.c:571-632).
+template <bool WIDE>
+__device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, unsigned char* win)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
     PairRec* rec = a.b.rec + pair;
     const int refBeg = rec->ref_begin1, readBeg = rec->read_begin1;
     const int score = rec->score1;
-    const int go = a.sc.go, ge = a.sc.ge;
 
     uint32_t* stage = reinterpret_cast<uint32_t*>(ws);                         // cigar ops, traceback order
-    int* Hrow = reinterpret_cast<int*>(ws + (size_t)a.cigar_stage_cap * 4);
-    // row buffers sized for the widest band that fits; direction matrix behind them
+    unsigned char* area = ws + (((size_t)a.cigar_stage_cap * 4 + 15) & ~(size_t)15);   // row buffers + direction matrix
     int nOps = 0;
     int status = 0;
 
@@ -46,129 +234,104 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws)
         if (lane == 0) stage[0] = cigar_pack(1, 0);
         nOps = 1;
     } else {
-        const int refLen = rec->ref_end1 - refBeg + 1;
-        const int readLen = rec->read_end1 - readBeg + 1;
-        const int8_t* ref = a.b.seqs + a.b.r_off[pair] + refBeg;
-        const int8_t* read = a.b.seqs + a.b.q_off[pair] + readBeg;
+        BandJob jb;
+        jb.refLen = rec->ref_end1 - refBeg + 1;
+        jb.readLen = rec->read_end1 - readBeg + 1;
+        jb.ref = a.b.seqs + a.b.r_off[pair] + refBeg;
+        jb.read = a.b.seqs + a.b.q_off[pair] + readBeg;
+        jb.go = a.sc.go; jb.ge = a.sc.ge; jb.mat = a.sc.mat;
+        const int readLen = jb.readLen, refLen = jb.refLen;
         int bw = refLen - readLen; if (bw < 0) bw = -bw; bw += 1;
-        int maxv = 0;
-        int Wd = 0;
+        int maxv = 0, rowStride = 0;
+        if (WIDE) { bw = -rec->cigar_len; maxv = (int)rec->cigar_off; }
         unsigned char* dir = nullptr;
         for (;;) {
-            Wd = 2 * bw + 1;
-            const long long rowBufBytes = ((long long)(2 * bw + 4) * 8 + 15) & ~15LL;
-            const long long need = rowBufBytes + (long long)Wd * readLen;
+            const int Wd = 2 * bw + 1;
+            jb.bw = bw;
+            int P = 0;                                           // diagonals per lane / 2; 0 = scan variant
+            if (Wd <= 64) P = 1; else if (Wd <= 128) P = 2; else if (Wd <= 256) P = 4;
+            else if (Wd <= 512) P = 8; else if (Wd <= 1024) P = 16;
+            if (!WIDE && (P == 0 || P > 2)) {
+                if (lane == 0) {
+                    rec->cigar_len = -bw; rec->cigar_off = maxv;
+                    a.next_idx[atomicAdd(a.next_count, 1)] = pair;
+                }
+                return;
+            }
+            rowStride = P ? 64 * P : ((Wd + 15) & ~15);
+            const long long rowBufBytes = P ? 0 : (((long long)(2 * bw + 4) * 8 + 15) & ~15LL);
+            const long long need = rowBufBytes + (long long)rowStride * readLen;
             if (need > a.dir_bytes) { status = PS_BAND_SCRATCH; break; }
-            int* Erow = Hrow + (2 * bw + 4);
-            dir = reinterpret_cast<unsigned char*>(Hrow) + rowBufBytes;
-            for (int k = lane; k < 2 * bw + 4; k += 32) { Hrow[k] = 0; Erow[k] = 0; }
-            __syncwarp();
-
-            for (int i = 0; i < readLen; ++i) {
-                const int beg = i - bw > 0 ? i - bw : 0;
-                const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
-                if (beg > end) break;                                   // the band has left the rectangle
-                const int W = end - beg + 1;
-                const int kk0 = beg - i + bw;                           // band diagonal of column beg
-                int rd = read[i]; if ((unsigned)rd > 4u) rd = 4;
-                // zeroed vertical neighbour of the last column (ssw.c:595-596): rows 1..w+1 whose band is
-                // clipped by the reference end in this row and the previous one
-                const bool quirk = i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;
-                unsigned char* drow = dir + (size_t)i * Wd;
-                int carryV = NEG_INF;                                   // running max of A(k) + k*ge over earlier chunks
-                int carryH = 0, carryF = 0;                             // H, F of the cell left of this chunk
-                for (int t0 = 0; t0 < W; t0 += 32) {
-                    const int t = t0 + lane;
-                    const bool act = t < W;
-                    const int kk = kk0 + t;
-                    const int j = beg + t;
-                    int Hd = 0, Hu = 0, Eu = 0, s = 0;
-                    if (act) {
-                        Hd = Hrow[kk]; Hu = Hrow[kk + 1]; Eu = Erow[kk + 1];
-                        if (quirk && j == refLen - 1) { Hu = 0; Eu = 0; }
-                        int rf = ref[j]; if ((unsigned)rf > 4u) rf = 4;
-                        s = a.sc.mat[rf * 5 + rd];
-                    }
-                    __syncwarp();
-                    const int eopen = Hu - go, eext = Eu - ge;
-                    const int E = eopen > eext ? eopen : eext;
-                    const int de = eopen > eext ? 1 : 0;
-                    const int e1 = E > 0 ? E : 0;
-                    const int dg = Hd + s;
-                    const int A = e1 > dg ? e1 : dg;                    // H without the horizontal gap (>= 0)
-                    // exclusive prefix max of V = A + t*ge
-                    int V = act ? A + t * ge : NEG_INF;
-                    int inc = V;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int o = __shfl_up_sync(FULL, inc, d);
-                        if (lane >= d && o > inc) inc = o;
-                    }
-                    int exc = __shfl_up_sync(FULL, inc, 1);
-                    if (lane == 0) exc = NEG_INF;
-                    if (carryV > exc) exc = carryV;
-                    // F(t) = max( -ge*(t+1), max_{k<t} (A(k) - go - (t-1-k)*ge) )
-                    int F = -ge * (t + 1);
-                    if (exc > NEG_INF) { const int f2 = exc - go - (t - 1) * ge; if (f2 > F) F = f2; }
-                    const int H = A > F ? A : F;
-                    // horizontal source: needs exact H, F of the left neighbour
-                    int Hl = __shfl_up_sync(FULL, H, 1), Fl = __shfl_up_sync(FULL, F, 1);
-                    if (lane == 0) { Hl = carryH; Fl = carryF; }
-                    const int df = (Hl - go > Fl - ge) ? 1 : 0;
-                    const int f1 = F > 0 ? F : 0;
-                    const int gapbest = e1 > f1 ? e1 : f1;
-                    int dh = 0;
-                    if (gapbest > dg) dh = e1 > f1 ? 1 : 2;
-                    if (act) {
-                        Hrow[kk] = H; Erow[kk] = E;
-                        drow[kk] = (unsigned char)(de | (df << 1) | (dh << 2));
-                        if (H > maxv) maxv = H;
-                    }
-                    carryV = __shfl_sync(FULL, inc, 31) > carryV ? __shfl_sync(FULL, inc, 31) : carryV;
-                    carryH = __shfl_sync(FULL, H, 31);
-                    carryF = __shfl_sync(FULL, F, 31);
-                    __syncwarp();
+            dir = area + rowBufBytes;
+            if (!WIDE) {
+                if (P == 1) maxv = band_fill_wave<1>(jb, dir, rowStride, maxv);
+                else maxv = band_fill_wave<2>(jb, dir, rowStride, maxv);
+            } else {
+                switch (P) {
+                    case 1: maxv = band_fill_wave<1>(jb, dir, rowStride, maxv); break;
+                    case 2: maxv = band_fill_wave<2>(jb, dir, rowStride, maxv); break;
+                    case 4: maxv = band_fill_wave<4>(jb, dir, rowStride, maxv); break;
+                    case 8: maxv = band_fill_wave<8>(jb, dir, rowStride, maxv); break;
+                    case 16: maxv = band_fill_wave<16>(jb, dir, rowStride, maxv); break;
+                    default: maxv = band_fill_scan(jb, reinterpret_cast<int*>(area), dir, rowStride, maxv); break;
                 }
             }
-            maxv = __reduce_max_sync(FULL, maxv);
             bw *= 2;
             if (!(maxv < score && bw < 2 * readLen)) break;
         }
         bw /= 2;
 
         if (!status) {
-            // traceback (lane 0): start in state H at the bottom-right corner, stop at read row 0
-            if (lane == 0) {
-                int i = readLen - 1, j = refLen - 1, state = 2;
-                int op = 0, prevOp = 0, run = 0;                         // 0 M, 1 I, 2 D
-                while (i > 0) {
-                    const int beg = i - bw > 0 ? i - bw : 0;
-                    const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
-                    if (j < beg || j > end) { status = PS_TRACEBACK_ERR; break; }
-                    const int d = dir[(size_t)i * Wd + (j - i + bw)];
-                    int code;
-                    if (state == 2) { const int dh = d >> 2; code = dh == 0 ? 1 : (dh == 1 ? 2 + (d & 1) : 4 + ((d >> 1) & 1)); }
-                    else if (state == 0) code = 2 + (d & 1);
-                    else code = 4 + ((d >> 1) & 1);
-                    switch (code) {
-                        case 1: --i; --j; state = 2; op = 0; break;
-                        case 2: --i; state = 0; op = 1; break;
-                        case 3: --i; state = 2; op = 1; break;
-                        case 4: --j; state = 1; op = 2; break;
-                        default: --j; state = 2; op = 2; break;
-                    }
-                    if (op == prevOp) ++run;
-                    else {
-                        if (nOps + 2 >= a.cigar_stage_cap) { status = PS_CIGAR_CAP; break; }
-                        stage[nOps++] = cigar_pack((uint32_t)run, prevOp);
-                        prevOp = op; run = 1;
+            __syncwarp();
+            // traceback: start in state H at the bottom-right corner, stop at read row 0 (ssw.c:636-696)
+            int i = readLen - 1, j = refLen - 1, state = 2;
+            int op = 0, prevOp = 0, run = 0;                                   // 0 M, 1 I, 2 D
+            int rowsPerWin = TB_WINDOW / rowStride; if (rowsPerWin < 1) rowsPerWin = 1;
+            const bool windowed = rowStride <= TB_WINDOW;
+            while (i > 0 && !status) {
+                // rows (lo, i] go to shared memory, then lane 0 walks until it leaves them
+                const int hi = i;
+                int lo = hi - rowsPerWin; if (lo < 0) lo = 0;                  // rows lo+1 .. hi
+                if (windowed) {
+                    const uint4* src = reinterpret_cast<const uint4*>(dir + (size_t)(lo + 1) * rowStride);
+                    const int n16 = (hi - lo) * rowStride / 16;
+                    for (int k = lane; k < n16; k += 32) reinterpret_cast<uint4*>(win)[k] = src[k];
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    while (i > lo) {
+                        const int beg = i - bw > 0 ? i - bw : 0;
+                        const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
+                        if (j < beg || j > end) { status = PS_TRACEBACK_ERR; break; }
+                        const int kk = j - i + bw;
+                        const int d = windowed ? win[(i - lo - 1) * rowStride + kk] : dir[(size_t)i * rowStride + kk];
+                        int code;
+                        if (state == 2) { const int dh = d >> 2; code = dh == 0 ? 1 : (dh == 1 ? 2 + (d & 1) : 4 + ((d >> 1) & 1)); }
+                        else if (state == 0) code = 2 + (d & 1);
+                        else code = 4 + ((d >> 1) & 1);
+                        switch (code) {
+                            case 1: --i; --j; state = 2; op = 0; break;
+                            case 2: --i; state = 0; op = 1; break;
+                            case 3: --i; state = 2; op = 1; break;
+                            case 4: --j; state = 1; op = 2; break;
+                            default: --j; state = 2; op = 2; break;
+                        }
+                        if (op == prevOp) ++run;
+                        else {
+                            if (nOps + 2 >= a.cigar_stage_cap) { status = PS_CIGAR_CAP; break; }
+                            stage[nOps++] = cigar_pack((uint32_t)run, prevOp);
+                            prevOp = op; run = 1;
+                        }
                     }
                 }
-                if (!status) {
-                    if (nOps + 2 >= a.cigar_stage_cap) status = PS_CIGAR_CAP;
-                    else if (op == 0) stage[nOps++] = cigar_pack((uint32_t)run + 1, 0);     // ssw.c:697-704
-                    else { stage[nOps++] = cigar_pack((uint32_t)run, op); stage[nOps++] = cigar_pack(1, 0); }
-                }
+                i = __shfl_sync(FULL, i, 0);
+                status = __shfl_sync(FULL, status, 0);
+                __syncwarp();
+            }
+            if (lane == 0 && !status) {
+                if (nOps + 2 >= a.cigar_stage_cap) status = PS_CIGAR_CAP;
+                else if (op == 0) stage[nOps++] = cigar_pack((uint32_t)run + 1, 0);     // ssw.c:697-704
+                else { stage[nOps++] = cigar_pack((uint32_t)run, op); stage[nOps++] = cigar_pack(1, 0); }
             }
             nOps = __shfl_sync(FULL, nOps, 0);
             status = __shfl_sync(FULL, status, 0);
@@ -191,8 +354,10 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws)
     }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(BAND_WARPS * 32) band_kernel(const BandArgs a)
 {
+    __shared__ uint4 window[BAND_WARPS][TB_WINDOW / 16];
     const int count = *a.wl.count;
     if (count <= 0) return;
     const int warp = threadIdx.x >> 5;
@@ -203,14 +368,15 @@ __global__ void __launch_bounds__(BAND_WARPS * 32) band_kernel(const BandArgs a)
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        band_pair(a, a.wl.idx[base + idx], ws);
+        band_pair<WIDE>(a, a.wl.idx[base + idx], ws, reinterpret_cast<unsigned char*>(window[warp]));
         __syncwarp();
     }
 }
 
-cudaError_t launch_band(const BandArgs& a, int blocks, cudaStream_t st)
+cudaError_t launch_band(bool wide, const BandArgs& a, int blocks, cudaStream_t st)
 {
-    band_kernel<<<blocks, BAND_WARPS * 32, 0, st>>>(a);
+    if (wide) band_kernel<true><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
+    else band_kernel<false><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -62,9 +62,12 @@ struct BandArgs {
     uint32_t* cigar_buf;           // device output buffer
     long long cigar_cap;
     unsigned long long* cigar_used;
+    int32_t* next_idx;             // narrow instance: pairs handed to the wide instance
+    int32_t* next_count;
 };
 constexpr int BAND_WARPS = 8;
-cudaError_t launch_band(const BandArgs& a, int blocks, cudaStream_t st);
+// wide = false: bands up to 128 diagonals; wide = true: everything the narrow launch handed over
+cudaError_t launch_band(bool wide, const BandArgs& a, int blocks, cudaStream_t st);
 
 // ---- DPX issue-rate probe (ssw_peak.cu)
 cudaError_t dpx_peak_probe(double* lane_instr_per_s, cudaStream_t st);

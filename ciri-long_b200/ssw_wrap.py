@@ -96,6 +96,8 @@ def _load():
     lib.ssw_batch_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64)]
     lib.ssw_batch_launch_count.restype = c_int64
     lib.ssw_batch_launch_count.argtypes = [c_void_p]
+    lib.ssw_batch_stage_ms.restype = c_int
+    lib.ssw_batch_stage_ms.argtypes = [c_void_p, c_void_p]
     lib.ssw_batch_destroy.restype = None
     lib.ssw_batch_destroy.argtypes = [c_void_p]
     lib.ssw_cuda_last_error.restype = c_char_p
@@ -157,6 +159,14 @@ class DeviceBatch(object):
         rc = self.libssw.ssw_batch_run(self.handle)
         if rc != 0:
             raise SSWCudaError("ssw_batch_run: %d %s" % (rc, self.libssw.ssw_cuda_last_error().decode()))
+
+    def stage_ms(self):
+        """device ms of (forward, deciding, reverse, cigar) stages of the last run()"""
+        ms = np.zeros(4, dtype=np.float32)
+        rc = self.libssw.ssw_batch_stage_ms(self.handle, ms.ctypes.data)
+        if rc != 0:
+            raise SSWCudaError("ssw_batch_stage_ms: %d" % rc)
+        return ms
 
     def launch_count(self):
         return int(self.libssw.ssw_batch_launch_count(self.handle))

@@ -196,3 +196,56 @@ def from_lists(queries, refs, params, name="list"):
     seqs, q_off, r_off = _pack(np.concatenate(queries).astype(np.int8), q_len,
                                np.concatenate(refs).astype(np.int8), r_len)
     return PairBatch(seqs, q_off, q_len, r_off, r_len, *params, name=name)
+
+
+def bsj_refinement_pairs_torch(n_pairs, device, seed=SEED_BASE + 2, ref_len=2000, q_min=300, q_max=800,
+                               n_frac=0.01, params=(1, 1, 1, 1), chunk=262144):
+    """Config C2 generated on the GPU with torch (same recipe as bsj_refinement_pairs, different RNG
+    stream): a million pairs take about a second instead of minutes.  Returns a PairBatch of numpy
+    arrays (host)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    parts_q, parts_r, qlens = [], [], []
+    for c0 in range(0, n_pairs, chunk):
+        n = min(chunk, n_pairs - c0)
+        refs = torch.randint(0, 4, (n, ref_len), dtype=torch.int8, device=device, generator=g)
+        ql0 = torch.randint(q_min, q_max + 1, (n,), device=device, generator=g)
+        start = (torch.rand(n, device=device, generator=g) * (ref_len - ql0 + 1).float()).long()
+        seg_start = torch.cumsum(ql0, 0) - ql0
+        total = int(ql0.sum())
+        base = torch.repeat_interleave(start + torch.arange(n, device=device) * ref_len - seg_start, ql0)
+        src = base + torch.arange(total, device=device)
+        codes = refs.reshape(-1)[src]
+        seg_id = torch.repeat_interleave(torch.arange(n, device=device), ql0)
+        u = torch.rand(total, device=device, generator=g)
+        keep = u >= 0.04
+        is_sub = keep & (u < 0.09)
+        shift = torch.randint(1, 4, (total,), dtype=torch.int8, device=device, generator=g)
+        codes = torch.where(is_sub, (codes + shift) % 4, codes)
+        runs = torch.where(torch.rand(total, device=device, generator=g) < 0.04,
+                           torch.randint(1, 4, (total,), device=device, generator=g), torch.zeros((), dtype=torch.long, device=device))
+        reps = keep.long() + runs
+        new = torch.repeat_interleave(codes, reps)
+        grp_start = torch.cumsum(reps, 0) - reps
+        pos = torch.arange(new.numel(), device=device) - torch.repeat_interleave(grp_start, reps)
+        inserted = pos >= torch.repeat_interleave(keep.long(), reps)
+        rnd = torch.randint(0, 4, (new.numel(),), dtype=torch.int8, device=device, generator=g)
+        new = torch.where(inserted, rnd, new)
+        if n_frac > 0:
+            new = torch.where(torch.rand(new.numel(), device=device, generator=g) < n_frac,
+                              torch.full((), 4, dtype=torch.int8, device=device), new)
+        new_len = torch.bincount(torch.repeat_interleave(seg_id, reps), minlength=n)
+        parts_q.append(new.cpu().numpy())
+        parts_r.append(refs.reshape(-1).cpu().numpy())
+        qlens.append(new_len.cpu().numpy().astype(np.int32))
+        del refs, codes, new, u, reps, pos, inserted, rnd, src, base, seg_id
+    q_len = np.concatenate(qlens)
+    r_len = np.full(n_pairs, ref_len, dtype=np.int32)
+    # layout: all queries, then all references (offsets are explicit, so any layout is legal)
+    q_codes = np.concatenate(parts_q)
+    r_codes = np.concatenate(parts_r)
+    q_off = (np.cumsum(q_len.astype(np.int64)) - q_len).astype(np.int64)
+    r_off = (len(q_codes) + np.arange(n_pairs, dtype=np.int64) * ref_len).astype(np.int64)
+    seqs = np.concatenate([q_codes, r_codes])
+    return PairBatch(seqs, q_off, q_len, r_off, r_len, *params, name="C2-bsj-refinement")

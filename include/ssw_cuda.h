@@ -129,6 +129,9 @@ int ssw_batch_run(ssw_batch* b);
 int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
 /* Number of kernel launches the last ssw_batch_run enqueued. */
 int64_t ssw_batch_launch_count(const ssw_batch* b);
+/* Device time (ms, CUDA events on the batch's stream) of the four stages of the last ssw_batch_run:
+ * forward score pass, deciding byte-flavour pass, reverse pass, CIGAR pass.  Waits for the run. */
+int ssw_batch_stage_ms(ssw_batch* b, float* ms4);
 void ssw_batch_destroy(ssw_batch* b);
 
 /* One-shot convenience: create + run + fetch + destroy on one device. */
