@@ -74,7 +74,6 @@ struct ssw_batch {
     int32_t* cursor2() const { return d_meta + 5 * N_LISTS; }
 };
 
-static int host_strip_height(int m) { return m <= VSTRIPS * KMAX ? (m + VSTRIPS - 1) / VSTRIPS : KMAX; }
 
 // Which scoring schemes the device recurrences reproduce bit-exactly (see ssw_score.cu header):
 // 5x5 matrix with a zero N row/column (the only matrix ssw_wrap.py:146-159 builds), gap_open >=
@@ -124,10 +123,10 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->max_q = std::max(b->max_q, m);
         b->max_r = std::max(b->max_r, r);
         if (m > 0 && r > 0) {
-            const int K = host_strip_height(m);
             const int kind = (b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255) ? 1 : 0;
+            const int K = strip_height_for(m, kind);
             b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
-            b->maxK = std::max(b->maxK, K);
+            b->maxK = std::max(b->maxK, std::max(K, strip_height_for(m, 0)));
             cig_cap += 2LL * m + 3;
         }
     }

@@ -13,6 +13,9 @@ constexpr int KMAX = 16;                        // max query rows per strip -> 1
 constexpr int LUT_ENTRIES = 625;                // (ref pair 25) x (query pair 25)
 constexpr int LUT_BYTES = LUT_ENTRIES * 32 * 4; // lane-replicated: bank == lane, conflict free
 constexpr int RP_STRIDE = 25 * 128;             // bytes between consecutive ref-pair rows of the LUT
+constexpr int RP_CHUNK = 512;                   // wavefront steps per staged chunk of ref-pair codes
+constexpr int RP_WINDOW = RP_CHUNK + 64;        // bytes of shared memory per warp for that chunk (+31 lanes of skew, +1 look-ahead)
+constexpr int SCORE_SMEM_BYTES = LUT_BYTES + SCORE_WARPS * RP_WINDOW;
 constexpr unsigned S16X2_MIN = 0x80008000u;
 constexpr int TRUNC_GATE = -16384;              // "minus infinity" that cannot wrap s16 when added to a score
 constexpr int TRUNC_SCORE_LIMIT = 16000;        // pairs scoring above this leave the truncated-F fast path
@@ -70,6 +73,12 @@ __device__ __forceinline__ unsigned addmax(unsigned a, unsigned b, unsigned c) {
 __device__ __forceinline__ unsigned addmax_relu(unsigned a, unsigned b, unsigned c) { return __viaddmax_s16x2_relu(a, b, c); }
 __device__ __forceinline__ unsigned max_relu(unsigned a, unsigned b) { return __vimax_s16x2_relu(a, b); }
 __device__ __forceinline__ unsigned max3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
+
+// shared-memory loads through 32-bit window addresses, and an address multiply-add that stays on the FMA
+// pipe (the DPX instructions own the ALU pipe in the score kernels)
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ unsigned mad_u32(unsigned a, unsigned b, unsigned c) { unsigned v; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(a), "r"(b), "r"(c)); return v; }
 
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return (unsigned)(lo & 0xffff) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffff); }

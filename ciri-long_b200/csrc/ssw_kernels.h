@@ -21,7 +21,7 @@ struct ScoreArgs {
 // bytes of scratch one warp needs for references of up to n_cap columns
 inline long long score_scratch_layout(int n_cap, long long* off_col, long long* off_bnd, long long* off_snap)
 {
-    long long o = ((long long)n_cap + 128 + 15) & ~15LL;   // ref-pair codes
+    long long o = 0;
     *off_col = o; o += (long long)n_cap * 4;               // column records (colmax | H last row)
     o = (o + 15) & ~15LL;
     *off_bnd = o; o += (long long)n_cap * 8;               // tile boundary (H, F, colmax)
@@ -30,6 +30,15 @@ inline long long score_scratch_layout(int n_cap, long long* off_col, long long* 
 }
 
 cudaError_t launch_score(int K, bool trunc, bool rev, const ScoreArgs& a, int blocks, cudaStream_t st);
+
+// strip height (template parameter K of the score kernel) for a query of m rows; must match ssw_score.cu
+__host__ __device__ inline int strip_height_for(int m, int trunc)
+{
+    if (!trunc) return m <= VSTRIPS * KMAX ? (m + VSTRIPS - 1) / VSTRIPS : KMAX;
+    const int segLen = (m + 7) / 8;
+    const int G = segLen > 8 * KMAX ? (segLen + KMAX - 1) / KMAX : 8;
+    return (segLen + G - 1) / G;
+}
 
 // ---- work-list construction (ssw_lists.cu)
 // list id = cls * 34 + kind * 17 + K   (cls: 0 normal / 1 long reference; kind: 0 GOTOH / 1 TRUNC; K: 1..16)

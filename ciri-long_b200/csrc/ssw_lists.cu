@@ -7,7 +7,9 @@
 
 namespace sswb {
 
-__device__ __forceinline__ int strip_height(int m) { return m <= VSTRIPS * KMAX ? (m + VSTRIPS - 1) / VSTRIPS : KMAX; }
+// rows per strip: GOTOH cuts the query into tiles of 64 equal strips; TRUNC gives each of the reference's
+// 8 segments (ceil(m/8) rows) its own G strips (ssw_score.cu)
+__device__ __forceinline__ int strip_height(int m, int kind) { return strip_height_for(m, kind); }
 
 // which list a pair belongs to in `stage`; -1 = not part of this stage
 __device__ int classify(int stage, const BatchView& b, const Scoring& sc, int long_thr, int p, int maxScore)
@@ -19,7 +21,7 @@ __device__ int classify(int stage, const BatchView& b, const Scoring& sc, int lo
         // the word flavour with gap_open == gap_extend has its own recurrence; it can only be reached when the
         // byte flavour can overflow at all: m * max(mat) + bias >= 255
         const int kind = (sc.go == sc.ge && (long long)m * maxScore + sc.bias >= 255) ? 1 : 0;
-        return list_id(n > long_thr ? 1 : 0, kind, strip_height(m));
+        return list_id(n > long_thr ? 1 : 0, kind, strip_height(m, kind));
     }
     // stage 1: reverse pass (ssw.c:834)
     if (rec->status & (PS_PUNT | PS_UNSUPPORTED)) return -1;
@@ -28,7 +30,7 @@ __device__ int classify(int stage, const BatchView& b, const Scoring& sc, int lo
     if (n <= 0) return -2;          // score 0: nothing to walk (handled inline by the caller)
     const int kind = (rec->word && sc.go == sc.ge) ? 1 : 0;
     // the scratch class follows the full reference length (as in the forward pass), not the trimmed one
-    return list_id(b.r_len[p] > long_thr ? 1 : 0, kind, strip_height(m));
+    return list_id(b.r_len[p] > long_thr ? 1 : 0, kind, strip_height(m, kind));
 }
 
 __device__ __forceinline__ int max_score(const Scoring& sc)

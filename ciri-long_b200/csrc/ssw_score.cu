@@ -4,45 +4,50 @@
 // for the reverse pass of ssw_align (ssw.c:836-849).  Not a port of the SSE2 code:
 //
 //   * inter-task parallelism, one warp per (query, reference) pair;
-//   * the query is cut into 64 "virtual strips" of K consecutive rows: lane t owns strip t in the low
+//   * the query is cut into "virtual strips" of up to K consecutive rows: lane t owns strip t in the low
 //     16-bit half and strip t+32 in the high half of every register, so each DPX instruction
-//     (VIADDMNMX.S16x2 / VIMNMX.S16x2) updates two cells;
+//     (VIADDMNMX.S16x2 / VIMNMX3.S16x2) updates two cells;
 //   * a systolic wavefront over the reference: at step s strip v computes column s-v; H, F and the
 //     running column maximum leave a strip through one rotate-shuffle per value and step;
 //   * substitution scores come from a lane-replicated (bank == lane, conflict free) shared-memory
 //     table indexed by (ref base pair, query base pair): one LDS per two cells, off the DPX pipe;
-//   * queries longer than 64*K rows are processed in row tiles that hand H/F/colmax to the next tile
-//     through a per-warp boundary array.
+//   * all scores are kept biased by +gap_open (H' = H + go, E' = E + go, F' = F + go): the floor of the
+//     local alignment becomes max(., go) inside a VIMNMX3, and H - gap_open is a plain 32-bit subtract of
+//     two halves that can never borrow, so it leaves the DPX pipe: 4 DPX instructions per two cells;
+//   * queries longer than one tile of 64 strips are processed in row tiles that hand H/F/colmax to the
+//     next tile through a per-warp boundary array.
 //
 // What is computed is the *semantics* of the reference, verified against oracle/ssw_oracle.c:
 //   GOTOH  plain affine-gap recurrences on the real query rows (equal to the reference's byte flavour,
 //          and to its word flavour when gap_open > gap_extend), the flavour (8/16 bit) being decided
-//          after the pass from max+bias >= 255 exactly like ssw.c:285,317,806;
+//          after the pass from max+bias >= 255 exactly like ssw.c:285,317,806.  The reference pads the
+//          query to a multiple of 16 (8) rows with zero-scoring rows that only influence maxColumn[];
+//          their contribution is added in closed form from the last real row (second_best()).
 //   TRUNC  the word flavour when gap_open == gap_extend: the reference's lazy-F loop stops after one
 //          step (ssw.c:467-478), so the vertical-gap chain is cut at every segment boundary
-//          (row % ceil(m/8) == 0) and only the boundary row's H sees the incoming F.
-// The reference pads the query to a multiple of 16 (8) rows with zero-scoring rows; those rows only
-// influence maxColumn[] (second-best score).  Their contribution is added in closed form from the
-// last real row (see second_best()), so the DP itself runs on real rows only.
+//          (row % ceil(m/8) == 0) and only the boundary row's H sees the incoming F.  Strips are aligned
+//          to the reference's 8 segments, so the cut always falls on the first row of a strip and only
+//          that row pays for it; a strip holds K or K-1 rows of its segment (the unused last row is
+//          skipped by selecting the hand-off from row K-2), and the reference's pad rows are simply the
+//          tail of the last segment.
 #include <stdio.h>
+#include <type_traits>
 #include "ssw_common.cuh"
 #include "ssw_kernels.h"
 
 namespace sswb {
 
 // Second-best score outside the mask window around the best end column (ssw.c:325-340 / 528-541).
-// colbuf[c] = colmax over the real query rows | H(last real row, c) << 16.  The reference's maxColumn[]
-// also covers P zero-scoring pad rows (P = L*ceil(m/L) - m, L = 16 byte / 8 word flavour).  A pad cell
-// is reached from the last real row by free diagonal steps plus at most one horizontal gap, so
+// colbuf[c] = (colmax + off) | (H(last real row, c) + off) << 16.  P > 0: the reference's maxColumn[] also
+// covers P zero-scoring pad rows that the DP did not compute.  A pad cell is reached from the last real
+// row by free diagonal steps plus at most one horizontal gap, so
 //   padmax(c) = max( max_{1<=d<=P} Hlast(c-d),  G(c) ),   G(c) = max(G(c-1) - ge, Hlast(c-P-1) - go, 0)
 // (vertical gaps are dominated inside the same column).  Lanes take contiguous column chunks; the
 // decaying chain G is stitched across chunks with one pass over the per-lane carries.
-__device__ __noinline__ void second_best(const unsigned* colbuf, int n, int m, int word, int endRef, int maskLen,
+__device__ __noinline__ void second_best(const unsigned* colbuf, int n, int P, int off, int word, int endRef, int maskLen,
                                          int go, int ge, int lane, int& score2, int& ref2)
 {
     const unsigned FULL = 0xffffffffu;
-    const int L = word ? 8 : 16;
-    const int P = ((m + L - 1) / L) * L - m;
     const int e1 = endRef - maskLen > 0 ? endRef - maskLen : 0;              // left region  [0, e1)
     int e2 = endRef + maskLen > n ? n : endRef + maskLen;                    // right region [e2, n)
     if (!word) e2 += 1;                                                      // ssw.c:334 vs ssw.c:536
@@ -54,7 +59,7 @@ __device__ __noinline__ void second_best(const unsigned* colbuf, int n, int m, i
     if (P > 0) {
         int carry = 0;
         for (int c = c0; c < c1; ++c) {
-            const int src = c - P - 1 >= 0 ? (int)(colbuf[c - P - 1] >> 16) - go : -1;
+            const int src = c - P - 1 >= 0 ? (int)(colbuf[c - P - 1] >> 16) - off - go : -1;
             carry = carry - ge > src ? carry - ge : src;
             if (carry < 0) carry = 0;
         }
@@ -69,14 +74,14 @@ __device__ __noinline__ void second_best(const unsigned* colbuf, int n, int m, i
     }
     int bv = 0, bi = 0x7fffffff, G = gin;
     for (int c = c0; c < c1; ++c) {
-        int mc = (int)(colbuf[c] & 0xffffu);
+        int mc = (int)(colbuf[c] & 0xffffu) - off;
         if (P > 0) {
-            const int src = c - P - 1 >= 0 ? (int)(colbuf[c - P - 1] >> 16) - go : -1;
+            const int src = c - P - 1 >= 0 ? (int)(colbuf[c - P - 1] >> 16) - off - go : -1;
             G = G - ge > src ? G - ge : src;
             if (G < 0) G = 0;
             int D = G;
             const int dmax = P < c ? P : c;
-            for (int d = 1; d <= dmax; ++d) { const int v = (int)(colbuf[c - d] >> 16); D = v > D ? v : D; }
+            for (int d = 1; d <= dmax; ++d) { const int v = (int)(colbuf[c - d] >> 16) - off; D = v > D ? v : D; }
             mc = D > mc ? D : mc;
         }
         if ((c < e1 || c >= e2) && mc > bv) { bv = mc; bi = c; }
@@ -87,8 +92,28 @@ __device__ __noinline__ void second_best(const unsigned* colbuf, int n, int m, i
     ref2 = M > 0 ? idx : 0;
 }
 
+// Row layout of one strip (see header): first query row, number of rows it holds, segment start flag.
+struct StripGeom { int first, live; bool valid, segStart; };
+
+template <int K, bool TRUNC>
+__device__ __forceinline__ StripGeom strip_geom(int v, int Vtot, int dead, int segLen, int G, int base, int extra)
+{
+    StripGeom s;
+    if (!TRUNC) {
+        s.first = v * K - dead;            // may be negative: zero rows in front of row 0
+        s.live = K; s.valid = true; s.segStart = false;
+    } else {
+        s.valid = v < Vtot;
+        const int l = v / G, g = v - l * G;
+        s.live = s.valid ? base + (g < extra ? 1 : 0) : 0;
+        s.first = l * segLen + g * base + (g < extra ? g : extra);
+        s.segStart = s.valid && g == 0 && l >= 1;
+    }
+    return s;
+}
+
 template <int K, bool TRUNC, bool REV>
-__device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, const unsigned* lut, unsigned char* ws)
+__device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, const unsigned* lut, unsigned char* rpw, unsigned char* ws)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
@@ -113,113 +138,143 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         qs = -1; rs = -1;
         terminate = rec->score1;
     }
+    const int go = a.sc.go, ge = a.sc.ge;
 
-    // per-warp scratch: [ref-pair codes | column records | tile boundary | best-column snapshots]
-    unsigned char* rpbuf = ws;
+    // per-warp scratch: [column records | tile boundary | best-column snapshots]
     unsigned* colbuf = reinterpret_cast<unsigned*>(ws + a.off_col);
     uint2* bnd = reinterpret_cast<uint2*>(ws + a.off_bnd);
     unsigned* snap = reinterpret_cast<unsigned*>(ws + a.off_snap);
 
-    // rpbuf[x], x = c + 32: code(c) * 5 + code(c - 32); columns outside [0, n) read as Z (score 0)
-    for (int x = lane; x < n + 96; x += 32) {
-        const int c = x - 32, c2 = x - 64;
-        int ca = 4, cb = 4;
-        if (c >= 0 && c < n) { ca = rb[(long long)c * rs]; if ((unsigned)ca > 4u) ca = 4; }
-        if (c2 >= 0 && c2 < n) { cb = rb[(long long)c2 * rs]; if ((unsigned)cb > 4u) cb = 4; }
-        rpbuf[x] = (unsigned char)(ca * 5 + cb);
+    // ---- strip layout
+    int T, Vtot, dead = 0, segLen = 0, G = 1, base = 0, extra = 0;
+    if (!TRUNC) {
+        const int rpt = VSTRIPS * K;
+        T = (m + rpt - 1) / rpt;
+        dead = T * rpt - m;
+        Vtot = T * VSTRIPS;
+    } else {
+        segLen = (m + 7) / 8;                                       // ssw.c:389
+        G = segLen > 8 * KMAX ? (segLen + KMAX - 1) / KMAX : 8;     // strips per segment
+        base = segLen / G; extra = segLen - base * G;
+        Vtot = 8 * G;
+        T = (Vtot + VSTRIPS - 1) / VSTRIPS;
+        if (base + (extra > 0 ? 1 : 0) != K) {                      // list construction and kernel disagree: never guess
+            if (lane == 0) rec->status |= PS_PUNT;
+            return;
+        }
     }
-    __syncwarp();
 
-    const int rpt = VSTRIPS * K;                      // rows per tile
-    const int T = (m + rpt - 1) / rpt;
-    const int dead = T * rpt - m;                      // zero rows in front of row 0 (right-aligned strips)
-    const int segLen = (m + 7) / 8;
-    const unsigned mgo = pack2(-a.sc.go, -a.sc.go), mge = pack2(-a.sc.ge, -a.sc.ge);
+    const unsigned GO = pack2(go, go);                              // bias of every stored score, and the local floor
+    const unsigned mge = pack2(-ge, -ge);
     const int src = (lane + 31) & 31;
-    const unsigned fix = lane == 0 ? 0x1044u : 0x3210u;   // lane 0: high half <- lane 31's low half, low half <- 0
-    const char* lutbase = reinterpret_cast<const char*>(lut) + lane * 4;
+    // lane 0: high half <- lane 31's low half, low half <- second operand (the bias for H/F, 0 for colmax)
+    const unsigned fix = lane == 0 ? 0x1054u : 0x3210u;
+    const unsigned lutS = (unsigned)__cvta_generic_to_shared(lut) + lane * 4;     // shared-window address of my LUT column
+    const unsigned rpS = (unsigned)__cvta_generic_to_shared(rpw) + 31 - lane;      // my slot of the ref-pair window at t = 0
+    const unsigned mtermP = pack2(-(terminate + go), -(terminate + go));
 
     int candM = 0, candCol = -1, candRow = 0;
     int termCol = -1, overCol = 0x7fffffff;
-    const unsigned mtermP = pack2(-terminate, -terminate);
 
     for (int p = 0; p < T; ++p) {
         const bool lastTile = (p == T - 1);
-        const int rowbase = p * rpt - dead;
-        const int r0lo = rowbase + lane * K, r0hi = rowbase + (lane + 32) * K;
+        const StripGeom sLo = strip_geom<K, TRUNC>(p * VSTRIPS + lane, Vtot, dead, segLen, G, base, extra);
+        const StripGeom sHi = strip_geom<K, TRUNC>(p * VSTRIPS + lane + 32, Vtot, dead, segLen, G, base, extra);
         unsigned qoff[K], E[K], Hd[K];
-        unsigned g[TRUNC ? K : 1], gF[TRUNC ? K : 1];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const int rl = r0lo + i, rh = r0hi + i;
+            const int rl = sLo.first + i, rh = sHi.first + i;
             int cl = 4, ch = 4;
-            if (rl >= 0) { cl = qb[(long long)rl * qs]; if ((unsigned)cl > 4u) cl = 4; }
-            if (rh >= 0) { ch = qb[(long long)rh * qs]; if ((unsigned)ch > 4u) ch = 4; }
-            qoff[i] = (unsigned)(cl * 5 + ch) * 128u;
-            E[i] = 0; Hd[i] = 0;
-            if (TRUNC) {
-                const bool bl = rl > 0 && (rl % segLen) == 0, bh = rh > 0 && (rh % segLen) == 0;
-                g[i] = pack2(bl ? TRUNC_GATE : 0, bh ? TRUNC_GATE : 0);
-                gF[i] = pack2(bl ? TRUNC_GATE : -a.sc.ge, bh ? TRUNC_GATE : -a.sc.ge);
-            }
+            if (rl >= 0 && rl < m && i < sLo.live) { cl = qb[(long long)rl * qs]; if ((unsigned)cl > 4u) cl = 4; }
+            if (rh >= 0 && rh < m && i < sHi.live) { ch = qb[(long long)rh * qs]; if ((unsigned)ch > 4u) ch = 4; }
+            qoff[i] = lutS + (unsigned)(cl * 5 + ch) * 128u;                // LUT address of this row pair for ref pair 0
+            E[i] = GO; Hd[i] = GO;
         }
-        unsigned Hout = 0, Fout = 0, R = 0, diagIn = 0, best = 0;
+        // TRUNC only: which halves take their hand-off from row K-1 (strip holds K rows) and which from row
+        // K-2 (K-1 rows); gates of the first row; strips past the end of the query do not count
+        const unsigned selMask = (sLo.live == K ? 0xffffu : 0u) | (sHi.live == K ? 0xffff0000u : 0u);
+        const unsigned stripMask = (sLo.valid ? 0xffffu : 0u) | (sHi.valid ? 0xffff0000u : 0u);
+        const unsigned g0 = pack2(sLo.segStart ? TRUNC_GATE : 0, sHi.segStart ? TRUNC_GATE : 0);
+        const unsigned gF0 = pack2(sLo.segStart ? TRUNC_GATE : -ge, sHi.segStart ? TRUNC_GATE : -ge);
+        // the strip whose hand-off is the complete column: colmax / H of the last row leave the tile there
+        const int wv = (TRUNC && lastTile) ? Vtot - 1 - p * VSTRIPS : VSTRIPS - 1;
+        const int wLane = wv & 31, wHalf = wv >> 5;
+
+        unsigned Hout = GO, Fout = GO, R = 0, diagIn = GO, best = GO;
         int bcolLo = -1, bcolHi = -1;
         int cLo = -lane, cHi = -lane - 32;
         int termflag = 0;
-        const int steps = n + 63;
-        unsigned rpCur = rpbuf[32 - lane];
-        unsigned rpNxt = rpbuf[33 - lane];
+        const int steps = n + wv;
+        const bool isWriter = lane == wLane;
+        const unsigned selW = wHalf ? 0x7632u : 0x5410u;                // (colmax, H last row) of the writer's half
+        unsigned* wcol = colbuf + (wHalf ? cHi : cLo);                  // the writer's column record at step 0
+        uint2* wbnd = bnd + cHi;
+        unsigned rpCur = 24u;                                           // ref-pair code of the current step (Z,Z before column 0)
 
-        for (int s = 0; s < steps; ++s) {
+        // One wavefront step at offset t of the current chunk.
+        //   CHECK = some lane may be outside [0, n) (pipeline fill and drain)
+        //   TOP   = strip 0 continues below the previous tile (reads the boundary array)
+        auto step = [&](auto chk, auto top, const int s, const int t) {
+            constexpr bool CHECK = decltype(chk)::value;
+            constexpr bool TOP = decltype(top)::value;
             // hand-off from the previous strip (computed one step ago, same column as ours now)
-            unsigned rH = __byte_perm(__shfl_sync(FULL, Hout, src), 0u, fix);
-            unsigned rF = __byte_perm(__shfl_sync(FULL, Fout, src), 0u, fix);
+            unsigned rH = __byte_perm(__shfl_sync(FULL, Hout, src), GO, fix);
+            unsigned rF = __byte_perm(__shfl_sync(FULL, Fout, src), GO, fix);
             unsigned rR = __byte_perm(__shfl_sync(FULL, R, src), 0u, fix);
-            if (p > 0 && lane == 0 && s < n) {           // strip 0 continues below the previous tile
-                const uint2 bv = bnd[s];
-                rH |= bv.x & 0xffffu; rF |= bv.x >> 16; rR |= bv.y & 0xffffu;
+            if (TOP) {
+                if (lane == 0 && s < n) {
+                    const uint2 bv = bnd[s];
+                    rH = (rH & 0xffff0000u) | (bv.x & 0xffffu);
+                    rF = (rF & 0xffff0000u) | (bv.x >> 16);
+                    rR = (rR & 0xffff0000u) | (bv.y & 0xffffu);
+                }
             }
             unsigned diag = diagIn;
             diagIn = rH;
             unsigned F = rF;
-            const char* sb = lutbase + rpCur * RP_STRIDE;
-            rpCur = rpNxt;
-            { int x = s + 34 - lane; x = x < n + 95 ? x : n + 95; rpNxt = rpbuf[x]; }
+            const unsigned rp = rpCur;
+            rpCur = lds_u8(rpS + t + 1);                                  // next step's code, one step ahead
 
-#ifdef SSW_DEBUG
-            if (rpCur > 24u) { printf("BAD rp %u pair %d lane %d s %d n %d m %d p %d K %d rev %d\n", rpCur, pair, lane, s, n, m, p, K, (int)REV); rpCur = 24; }
-#endif
-            unsigned mx = 0, hprev = 0;
+            unsigned mx = 0, hprev = 0, Hk2 = rH, Fk2 = rF;
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-#ifdef SSW_DEBUG
-                if (qoff[i] > 3072u) { printf("BAD qoff %u pair %d lane %d i %d\n", qoff[i], pair, lane, i); }
-#endif
-                const unsigned sc = *reinterpret_cast<const unsigned*>(sb + qoff[i]);
-                const unsigned x = addmax(diag, sc, E[i]);
-                const unsigned h = max_relu(x, F);
+                const unsigned sc = lds_u32(mad_u32(rp, RP_STRIDE, qoff[i]));
+                const unsigned x = addmax(diag, sc, E[i]);                    // max(Hdiag + s, E)
+                const unsigned h = max3(x, F, GO);                            // H (floor 0 == bias)
                 unsigned u;
-                if (TRUNC) {
-                    const unsigned h0 = addmax_relu(F, g[i], x);
-                    u = addmax(h0, mgo, S16X2_MIN);
-                    F = addmax(F, gF[i], u);
+                if (TRUNC && i == 0) {
+                    // first row of a strip: if it starts a segment the incoming F reaches H only
+                    const unsigned tt = addmax(F, g0, x);
+                    const unsigned h0 = max3(tt, GO, GO);
+                    u = h0 - GO;
+                    F = addmax(F, gF0, u);
                 } else {
-                    u = addmax(h, mgo, S16X2_MIN);
+                    u = h - GO;                                               // H - gap_open: halves cannot borrow
                     F = addmax(F, mge, u);
                 }
                 E[i] = addmax(E[i], mge, u);
                 diag = Hd[i];
                 Hd[i] = h;
-                if (i & 1) mx = max3(mx, hprev, h);
-                hprev = h;
+                if (TRUNC && i == K - 2) { Hk2 = h; Fk2 = F; }
+                const unsigned hm = (TRUNC && i == K - 1) ? (h & selMask) : h;  // an unused last row does not count
+                if (i & 1) mx = max3(mx, hprev, hm);
+                hprev = hm;
             }
             if (K & 1) mx = max_relu(mx, hprev);
-            Hout = Hd[K - 1];
-            Fout = F;
+            if (TRUNC) {
+                Hout = (Hd[K - 1] & selMask) | (Hk2 & ~selMask);
+                Fout = (F & selMask) | (Fk2 & ~selMask);
+            } else {
+                Hout = Hd[K - 1];
+                Fout = F;
+            }
 
-            const unsigned vm = ((unsigned)cLo < (unsigned)n ? 0xffffu : 0u) | ((unsigned)cHi < (unsigned)n ? 0xffff0000u : 0u);
-            unsigned mxv = mx & vm;
+            unsigned mxv = mx;
+            if (CHECK) {
+                const unsigned vm = ((unsigned)cLo < (unsigned)n ? 0xffffu : 0u) | ((unsigned)cHi < (unsigned)n ? 0xffff0000u : 0u);
+                mxv &= vm;
+            }
+            if (TRUNC) mxv &= stripMask;
             R = max_relu(rR, mxv);
             if (REV) {
                 // The reference stops at the first column whose maximum equals score1 (ssw.c:296,499), so
@@ -249,23 +304,63 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 }
                 best = nb;
             }
-            if (lane == 31 && (unsigned)cHi < (unsigned)n) {
-                if (!lastTile) {
-                    bnd[cHi] = make_uint2(__byte_perm(Hout, Fout, 0x7632u), R >> 16);
-                } else if (!REV) {
-                    colbuf[cHi] = __byte_perm(R, Hout, 0x7632u);           // colmax | H(last row) << 16
-                } else if (!termflag && (int)(R >> 16) == terminate) {
-                    termflag = 1; termCol = cHi;
-                }
+            // the complete column leaves the tile at the writer strip
+            const unsigned wval = __byte_perm(R, Hout, selW);               // colmax | H(last row) << 16 of the writer's half
+            bool colOk = isWriter;
+            if (CHECK) colOk = colOk && (unsigned)(wHalf ? cHi : cLo) < (unsigned)n;
+            if (!lastTile) {
+                if (colOk) wbnd[s] = make_uint2(__byte_perm(Hout, Fout, 0x7632u), R >> 16);   // always strip 63: high halves
+            } else if (!REV) {
+                if (colOk) wcol[s] = wval;
+            } else if (colOk && !termflag && (int)(wval & 0xffffu) == terminate + go) {
+                termflag = 1; termCol = wHalf ? cHi : cLo;
             }
             ++cLo; ++cHi;
-            if (REV && lastTile && (s & 7) == 7) {
-                if (__any_sync(FULL, termflag)) break;
+        };
+
+        // Steps run in chunks of RP_CHUNK: the warp first stages the ref-pair codes of the chunk
+        // (code(c) * 5 + code(c - 32), Z outside [0, n)) in its shared-memory window, then sweeps it.
+        // Chunk borders fall on the phase borders: pipeline fill [0, 63), steady state [63, n), drain [n, steps).
+        const int sA = steps < 63 ? steps : 63;
+        int sB = n < steps ? n : steps; if (sB < sA) sB = sA;
+        auto sweep = [&](auto top) {
+            int s0 = 0;
+            bool stop = false;
+            while (s0 < steps && !stop) {
+                int s1 = s0 + RP_CHUNK < steps ? s0 + RP_CHUNK : steps;
+                if (s0 < sA) { if (s1 > sA) s1 = sA; }
+                else if (s0 < sB) { if (s1 > sB) s1 = sB; }
+                const bool steady = s0 >= sA && s1 <= sB;
+                __syncwarp();
+                for (int x = lane; x < s1 - s0 + 32; x += 32) {
+                    const int c = s0 - 31 + x, c2 = c - 32;
+                    int ca = 4, cb = 4;
+                    if (c >= 0 && c < n) { ca = rb[(long long)c * rs]; if ((unsigned)ca > 4u) ca = 4; }
+                    if (c2 >= 0 && c2 < n) { cb = rb[(long long)c2 * rs]; if ((unsigned)cb > 4u) cb = 4; }
+                    rpw[x] = (unsigned char)(ca * 5 + cb);
+                }
+                __syncwarp();
+                rpCur = lds_u8(rpS);                                        // code of step s0 for my column
+                const int len = s1 - s0;
+                if (steady) {
+#pragma unroll 2
+                    for (int t = 0; t < len; ++t) {
+                        step(std::false_type{}, top, s0 + t, t);
+                        if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
+                    }
+                } else {
+                    for (int t = 0; t < len; ++t) {
+                        step(std::true_type{}, top, s0 + t, t);
+                        if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
+                    }
+                }
+                s0 = s1;
             }
-        }
+        };
+        if (p > 0) sweep(std::true_type{}); else sweep(std::false_type{});
 
         // ---- tile epilogue: best cell of this tile in reference order (max, first column, first row)
-        const int vlo = lo16(best), vhi = hi16(best);
+        const int vlo = lo16(best) - go, vhi = hi16(best) - go;
         const int M = __reduce_max_sync(FULL, vlo > vhi ? vlo : vhi);
         if (M > 0) {
             const int clo = vlo == M ? bcolLo : 0x7fffffff, chi = vhi == M ? bcolHi : 0x7fffffff;
@@ -275,14 +370,17 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             const int owner = strip & 31, half = strip >> 5;
             int row = 0;
             if (lane == owner) {
-                for (int i = K - 1; i >= 0; --i) {
+                const StripGeom sg = half ? sHi : sLo;
+                for (int i = sg.live - 1; i >= 0; --i) {
                     const unsigned v = snap[(half * K + i) * 32 + lane];
-                    if ((half ? hi16(v) : lo16(v)) == M) row = rowbase + strip * K + i;
+                    if ((half ? hi16(v) : lo16(v)) - go == M) row = sg.first + i;
                 }
+                if (row > m - 1) row = m - 1;                           // pad rows never lower end_read (ssw.c:144,306)
             }
             row = __shfl_sync(FULL, row, owner);
             if (M > candM || (M == candM && col < candCol)) { candM = M; candCol = col; candRow = row; }
         }
+        if (lastTile) termCol = __shfl_sync(FULL, termCol, wLane);
         __syncwarp();      // boundary array / snapshots written by this tile are read by the next one
     }
 
@@ -294,11 +392,11 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             // second look at a pair whose truncated pass stayed below the 8-bit limit: the byte flavour is
             // authoritative unless it overflows, in which case the word result already stored stands.
             if (over8) { if (lane == 0) rec->status &= ~PS_NEED_GOTOH; return; }
-        } else if (!TRUNC && over8 && a.sc.go == a.sc.ge) {
+        } else if (!TRUNC && over8 && go == ge) {
             status |= PS_PUNT;          // host routing guarantees this cannot happen; never guess
         }
         if (TRUNC && !over8) status |= PS_NEED_GOTOH;
-        if (candM >= (TRUNC ? TRUNC_SCORE_LIMIT : S16_SCORE_LIMIT)) status |= PS_PUNT;
+        if (candM >= (TRUNC ? TRUNC_SCORE_LIMIT : S16_SCORE_LIMIT) - go) status |= PS_PUNT;
 
         const int endRef = candM > 0 ? candCol : (word ? 0 : -1);  // ssw.c:145 vs ssw.c:388
         const int endRead = candM > 0 ? candRow : 0;
@@ -306,7 +404,10 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         const int maskLen = a.b.mask_len[pair];
         if (maskLen >= 15) {                                        // ssw.c:826-832
             ref2 = 0;
-            second_best(colbuf, n, m, word, endRef, maskLen, a.sc.go, a.sc.ge, lane, score2, ref2);
+            // TRUNC computed the reference's pad rows itself; GOTOH adds them here for the flavour that won
+            const int L = word ? 8 : 16;
+            const int P = TRUNC ? 0 : ((m + L - 1) / L) * L - m;
+            second_best(colbuf, n, P, go, word, endRef, maskLen, go, ge, lane, score2, ref2);
         }
         if (lane == 0) {
             rec->score1 = candM; rec->score2 = score2;
@@ -324,7 +425,6 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         int status = 0;
         // a cell above score1 before the stop column (or with no stop column at all): the truncated-F
         // flavour scored the prefix higher than the forward pass did; the exact kernel decides
-        termCol = __shfl_sync(FULL, termCol, 31);
         overCol = __reduce_min_sync(FULL, overCol);
         if (overCol != 0x7fffffff && (termCol < 0 || overCol <= termCol)) status |= PS_PUNT;
         if (lane == 0) {
@@ -353,13 +453,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreArgs
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int base = a.wl.base ? *a.wl.base : 0;
+    unsigned char* rpw = reinterpret_cast<unsigned char*>(lut) + LUT_BYTES + warp * RP_WINDOW;
     unsigned char* ws = a.scratch + (size_t)(blockIdx.x * SCORE_WARPS + warp) * a.scratch_stride;
     for (;;) {
         int idx = 0;
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        score_pair<K, TRUNC, REV>(a, a.wl.idx[base + idx], lut, ws);
+        score_pair<K, TRUNC, REV>(a, a.wl.idx[base + idx], lut, rpw, ws);
         __syncwarp();
     }
 }
@@ -374,11 +475,11 @@ static cudaError_t launch_one(const ScoreArgs& a, int blocks, cudaStream_t st)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(score_kernel<K, TRUNC, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(score_kernel<K, TRUNC, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCORE_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    score_kernel<K, TRUNC, REV><<<blocks, SCORE_THREADS, LUT_BYTES, st>>>(a);
+    score_kernel<K, TRUNC, REV><<<blocks, SCORE_THREADS, SCORE_SMEM_BYTES, st>>>(a);
     return cudaGetLastError();
 }
 
