@@ -43,67 +43,80 @@ struct BandJob {
 };
 
 // ---- wavefront variant: 32 lanes x DPL diagonals, one row per lane and iteration -------------------
-template <int P>
-__device__ __forceinline__ int band_fill_wave(const BandJob& jb, unsigned char* dir, int rowStride, int maxv)
+// stab: shared table, stab[rd] = the five substitution scores against read base rd packed as bytes
+// (A C G T in .x, N in .y); a cell picks its score with one PRMT whose selector (base * 0x1111 + 0x8880:
+// byte index + sign replication) travels with the diagonal instead of the base code.
+// QUIRK = the band can be clipped by the reference end within the first w+1 rows (ssw.c:595-596 applies).
+template <int P, bool QUIRK>
+__device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, const int8_t* __restrict__ read,
+                                              const int refLen, const int readLen, const int bw, const int go, const int ge,
+                                              const uint2* stab, unsigned char* dir, const int rowStride, int maxv)
 {
     constexpr int DPL = 2 * P;
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
-    const int bw = jb.bw, go = jb.go, ge = jb.ge, refLen = jb.refLen, readLen = jb.readLen;
     const int kkBase = lane * DPL;
-    int Hp[DPL], Ep[DPL], rc[DPL];
+    int Hp[DPL], Ep[DPL];
+    unsigned sel[DPL];
     {
-        const int i0 = -lane;                                   // row of iteration 0
+        const int j0 = -lane + kkBase - bw;                     // column of my first diagonal in the row of iteration 0
 #pragma unroll
         for (int d = 0; d < DPL; ++d) {
             Hp[d] = 0; Ep[d] = 0;
-            const int j = i0 + kkBase + d - bw;
-            int c = 4;
-            if (j >= 0 && j < refLen) { c = jb.ref[j]; if ((unsigned)c > 4u) c = 4; }
-            rc[d] = c;
+            const int j = j0 + d;
+            unsigned c = 4;
+            if (j >= 0 && j < refLen) { c = (unsigned)ref[j]; if (c > 4u) c = 4; }
+            sel[d] = c * 0x1111u + 0x8880u;
         }
     }
     int lastH = 0, lastF = 0;                                   // H, F of my last diagonal in the row I just finished
     const int iters = readLen + 31;
+    int i = -lane;                                              // my row in this iteration
+    int jFirst = -lane + kkBase - bw;                           // column of my first diagonal in row i
+    const int8_t* nextRef = ref + jFirst + DPL;                 // base entering my last diagonal in the next row
+    unsigned char* drow = dir + (long long)i * rowStride + kkBase;
     for (int r = 0; r < iters; ++r) {
-        const int i = r - lane;
-        const bool rowOk = i >= 0 && i < readLen;
+        const bool rowOk = (unsigned)i < (unsigned)readLen;
         // left neighbour of my block: lane-1's last cell of the same row (computed one iteration ago)
         int Hl = __shfl_up_sync(FULL, lastH, 1), Fl = __shfl_up_sync(FULL, lastF, 1);
         if (lane == 0) { Hl = 0; Fl = 0; }
-        int rd = 4;
-        if (rowOk) { rd = jb.read[i]; if ((unsigned)rd > 4u) rd = 4; }
-        const bool quirk = i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;   // ssw.c:595-596
+        unsigned rd = 4;
+        if (rowOk) { rd = (unsigned)read[i]; if (rd > 4u) rd = 4; }
+        const uint2 srow = stab[rd];
+        // columns of this row inside band and rectangle: beg <= j <= end  <=>  (unsigned)(j - beg) <= span
+        const int beg = i - bw > 0 ? i - bw : 0;
+        const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
+        const bool rowHas = rowOk && end >= beg;                 // rows past the band's reach hold no cell
+        const int span = rowHas ? end - beg : 0;
+        const int jrel = rowHas ? jFirst - beg : -(1 << 30);      // (unsigned) of a negative never passes the test
+        const bool quirk = QUIRK && i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;
+        const int jq = refLen - 1 - jFirst;                     // diagonal slot that sits on the last column
         unsigned dirw[(DPL + 3) / 4];
 #pragma unroll
         for (int w = 0; w < (DPL + 3) / 4; ++w) dirw[w] = 0;
         int upH = 0, upE = 0;                                   // (i-1, first diagonal of lane+1), known after d == 0
 #pragma unroll
         for (int d = 0; d < DPL; ++d) {
-            const int kk = kkBase + d;
-            const int j = i + kk - bw;
-            const bool valid = rowOk && kk <= 2 * bw && j >= 0 && j < refLen;
+            const bool valid = (unsigned)(jrel + d) <= (unsigned)span;
             int Hu, Eu;
             if (d + 1 < DPL) { Hu = Hp[d + 1]; Eu = Ep[d + 1]; }
             else { Hu = upH; Eu = upE; }
-            if (quirk && j == refLen - 1) { Hu = 0; Eu = 0; }
-            const int s = jb.mat[rc[d] * 5 + rd];
+            if (QUIRK) { if (quirk && d == jq) { Hu = 0; Eu = 0; } }
+            const int s = (int)prmt_raw(srow.x, srow.y, sel[d]);
             const int eopen = Hu - go, eext = Eu - ge;
             const int E = eopen > eext ? eopen : eext;
-            const int de = eopen > eext ? 1 : 0;
             const int fopen = Hl - go, fext = Fl - ge;
             const int F = fopen > fext ? fopen : fext;
-            const int df = fopen > fext ? 2 : 0;
             const int e1 = E > 0 ? E : 0, f1 = F > 0 ? F : 0;
             const int gapbest = e1 > f1 ? e1 : f1;
             const int dg = Hp[d] + s;
             int H = gapbest > dg ? gapbest : dg;
-            int dh = 0;
-            if (gapbest > dg) dh = e1 > f1 ? 4 : 8;
+            unsigned code = (eopen > eext ? 1u : 0u) | (fopen > fext ? 2u : 0u);
+            if (gapbest > dg) code |= e1 > f1 ? 4u : 8u;
             int Eo = E, Fo = F;
             if (!valid) { H = 0; Eo = 0; Fo = 0; }
-            else if (H > maxv) maxv = H;
-            dirw[d >> 2] |= (unsigned)(de | df | dh) << (8 * (d & 3));
+            maxv = H > maxv ? H : maxv;
+            dirw[d >> 2] |= code << (8 * (d & 3));
             Hp[d] = H; Ep[d] = Eo;
             Hl = H; Fl = Fo;
             if (d == 0) {
@@ -116,25 +129,25 @@ __device__ __forceinline__ int band_fill_wave(const BandJob& jb, unsigned char* 
         }
         lastH = Hl; lastF = Fl;
         if (rowOk) {
-            unsigned char* p = dir + (size_t)i * rowStride + kkBase;
-            if (DPL == 2) *reinterpret_cast<unsigned short*>(p) = (unsigned short)dirw[0];
-            else if (DPL == 4) *reinterpret_cast<unsigned*>(p) = dirw[0];
-            else if (DPL == 8) *reinterpret_cast<uint2*>(p) = make_uint2(dirw[0], dirw[1]);
+            if (DPL == 2) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)dirw[0];
+            else if (DPL == 4) *reinterpret_cast<unsigned*>(drow) = dirw[0];
+            else if (DPL == 8) *reinterpret_cast<uint2*>(drow) = make_uint2(dirw[0], dirw[1]);
             else {
 #pragma unroll
                 for (int w = 0; w < DPL / 16; ++w)
-                    reinterpret_cast<uint4*>(p)[w] = make_uint4(dirw[4 * w], dirw[4 * w + 1], dirw[4 * w + 2], dirw[4 * w + 3]);
+                    reinterpret_cast<uint4*>(drow)[w] = make_uint4(dirw[4 * w], dirw[4 * w + 1], dirw[4 * w + 2], dirw[4 * w + 3]);
             }
         }
         // next row: every diagonal moves one reference base to the right
 #pragma unroll
-        for (int d = 0; d + 1 < DPL; ++d) rc[d] = rc[d + 1];
+        for (int d = 0; d + 1 < DPL; ++d) sel[d] = sel[d + 1];
         {
-            const int j = i + 1 + kkBase + DPL - 1 - bw;
-            int c = 4;
-            if (j >= 0 && j < refLen) { c = jb.ref[j]; if ((unsigned)c > 4u) c = 4; }
-            rc[DPL - 1] = c;
+            const int j = jFirst + DPL;
+            unsigned c = 4;
+            if ((unsigned)j < (unsigned)refLen) { c = (unsigned)*nextRef; if (c > 4u) c = 4; }
+            sel[DPL - 1] = c * 0x1111u + 0x8880u;
         }
+        ++i; ++jFirst; ++nextRef; drow += rowStride;
     }
     return __reduce_max_sync(FULL, maxv);
 }
@@ -215,7 +228,7 @@ __device__ int band_fill_scan(const BandJob& jb, int* Hrow, unsigned char* dir, 
 // past that is handed to the WIDE instance (its own launch) together with the band width reached and the
 // running maximum, which is all the doubling loop carries from one width to the next (ssw.c:571-632).
 template <bool WIDE>
-__device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, unsigned char* win)
+__device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, unsigned char* win, const uint2* stab)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
@@ -263,19 +276,24 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
             const long long need = rowBufBytes + (long long)rowStride * readLen;
             if (need > a.dir_bytes) { status = PS_BAND_SCRATCH; break; }
             dir = area + rowBufBytes;
+            // ssw.c:595-596 can only matter if the band reaches the last column within the first w+1 rows
+            const bool q = 2 * bw + 1 >= refLen - 1;
+#define SSW_WAVE(PP) (q ? band_fill_wave<PP, true>(jb.ref, jb.read, refLen, readLen, bw, jb.go, jb.ge, stab, dir, rowStride, maxv) \
+                        : band_fill_wave<PP, false>(jb.ref, jb.read, refLen, readLen, bw, jb.go, jb.ge, stab, dir, rowStride, maxv))
             if (!WIDE) {
-                if (P == 1) maxv = band_fill_wave<1>(jb, dir, rowStride, maxv);
-                else maxv = band_fill_wave<2>(jb, dir, rowStride, maxv);
+                if (P == 1) maxv = SSW_WAVE(1);
+                else maxv = SSW_WAVE(2);
             } else {
                 switch (P) {
-                    case 1: maxv = band_fill_wave<1>(jb, dir, rowStride, maxv); break;
-                    case 2: maxv = band_fill_wave<2>(jb, dir, rowStride, maxv); break;
-                    case 4: maxv = band_fill_wave<4>(jb, dir, rowStride, maxv); break;
-                    case 8: maxv = band_fill_wave<8>(jb, dir, rowStride, maxv); break;
-                    case 16: maxv = band_fill_wave<16>(jb, dir, rowStride, maxv); break;
+                    case 1: maxv = SSW_WAVE(1); break;
+                    case 2: maxv = SSW_WAVE(2); break;
+                    case 4: maxv = SSW_WAVE(4); break;
+                    case 8: maxv = SSW_WAVE(8); break;
+                    case 16: maxv = SSW_WAVE(16); break;
                     default: maxv = band_fill_scan(jb, reinterpret_cast<int*>(area), dir, rowStride, maxv); break;
                 }
             }
+#undef SSW_WAVE
             bw *= 2;
             if (!(maxv < score && bw < 2 * readLen)) break;
         }
@@ -358,8 +376,17 @@ template <bool WIDE>
 __global__ void __launch_bounds__(BAND_WARPS * 32) band_kernel(const BandArgs a)
 {
     __shared__ uint4 window[BAND_WARPS][TB_WINDOW / 16];
+    __shared__ uint2 stab[8];
     const int count = *a.wl.count;
     if (count <= 0) return;
+    if (threadIdx.x < 5) {
+        // scores of read base rd = threadIdx.x against ref bases A C G T (bytes of .x) and N (.y)
+        const int rd = threadIdx.x;
+        unsigned lo = 0;
+        for (int rf = 0; rf < 4; ++rf) lo |= (unsigned)(unsigned char)a.sc.mat[rf * 5 + rd] << (8 * rf);
+        stab[rd] = make_uint2(lo, (unsigned)(unsigned char)a.sc.mat[4 * 5 + rd]);
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int base = a.wl.base ? *a.wl.base : 0;
     unsigned char* ws = a.scratch + (size_t)(blockIdx.x * BAND_WARPS + warp) * a.scratch_stride;
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32) band_kernel(const BandArgs a)
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        band_pair<WIDE>(a, a.wl.idx[base + idx], ws, reinterpret_cast<unsigned char*>(window[warp]));
+        band_pair<WIDE>(a, a.wl.idx[base + idx], ws, reinterpret_cast<unsigned char*>(window[warp]), stab);
         __syncwarp();
     }
 }

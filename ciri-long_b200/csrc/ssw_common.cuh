@@ -80,6 +80,10 @@ __device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm vol
 __device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ unsigned mad_u32(unsigned a, unsigned b, unsigned c) { unsigned v; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(a), "r"(b), "r"(c)); return v; }
 
+// prmt.b32 with the full selector (bit 3 of a nibble replicates the sign of the selected byte); the CUDA
+// intrinsic __byte_perm masks the selector with 0x7777 and loses that mode
+__device__ __forceinline__ unsigned prmt_raw(unsigned a, unsigned b, unsigned sel) { unsigned v; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(a), "r"(b), "r"(sel)); return v; }
+
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return (unsigned)(lo & 0xffff) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffff); }
 __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
