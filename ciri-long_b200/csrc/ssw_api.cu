@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,13 @@
 using namespace sswb;
 
 static thread_local std::string g_last_error;
+// SSW_CUDA_TRACE=1: print host-side phase timings of the batch calls to stderr (diagnostics)
+static bool trace_on() { static int v = -1; if (v < 0) { const char* e = getenv("SSW_CUDA_TRACE"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+struct TraceTimer {
+    const char* what; std::chrono::steady_clock::time_point t0;
+    explicit TraceTimer(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {}
+    ~TraceTimer() { if (trace_on()) fprintf(stderr, "[ssw_cuda] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
 static void set_error(const std::string& s) { g_last_error = s; }
 extern "C" const char* ssw_cuda_last_error(void) { return g_last_error.c_str(); }
 
@@ -34,6 +42,27 @@ extern "C" const char* ssw_cuda_last_error(void) { return g_last_error.c_str(); 
         }                                                                                     \
     } while (0)
 
+// Device memory comes from the stream-ordered allocator with an unbounded release threshold, so that
+// repeated batches (the e2e path creates one per chunk) reuse their buffers instead of paying cudaMalloc.
+static cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_ready[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+template <typename T> static cudaError_t dev_alloc_t(T** p, size_t count, cudaStream_t st) { return dev_alloc((void**)p, count * sizeof(T), st); }
+static void dev_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
 static const int LONG_REF_THRESHOLD = 32768;          // references longer than this get their own scratch class
 static const long long SCRATCH_BUDGET = 3LL << 30;    // bytes of score-pass scratch per class
 
@@ -44,7 +73,10 @@ struct ssw_batch {
     int32_t n = 0;
     int sms = 0;
     Scoring sc;
-    // inputs
+    // inputs (d_seqs holds bytes [seq_lo, seq_hi) of the caller's buffer; kernels index it through
+    // d_seqs - seq_lo so the caller's offsets are used unchanged)
+    long long seq_lo = 0, seq_hi = 0;
+    std::vector<int32_t> h_mask;
     int8_t* d_seqs = nullptr;
     long long *d_qoff = nullptr, *d_roff = nullptr;
     int32_t *d_qlen = nullptr, *d_rlen = nullptr, *d_mask = nullptr;
@@ -55,11 +87,14 @@ struct ssw_batch {
     unsigned char* d_sscr[2] = {nullptr, nullptr};
     long long sstride[2] = {0, 0}, off_col[2] = {0, 0}, off_bnd[2] = {0, 0}, off_snap[2] = {0, 0};
     int sblocks[2] = {0, 0};
-    unsigned char* d_bscr = nullptr;
+    unsigned char* d_bscr = nullptr;                 // CIGAR pass, narrow instance (bands up to 128 diagonals)
     long long bstride = 0, bdir = 0;
     int bblocks = 0, bstage = 0;
+    unsigned char* d_wscr = nullptr;                 // CIGAR pass, wide instance (few pairs, big direction matrices)
+    long long wstride = 0, wdir = 0;
+    int wblocks = 0;
     uint32_t* d_cigar = nullptr;
-    long long cigar_cap = 0;
+    long long cigar_cap = 0, cigar_worst = 0;
     unsigned long long* d_cigar_used = nullptr;
     // host-side shape summary
     int max_q = 0, max_r = 0, maxK = 0;
@@ -68,7 +103,7 @@ struct ssw_batch {
     std::vector<PairRec> h_rec;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last run
 
-    BatchView view() const { return BatchView{d_seqs, d_qoff, d_qlen, d_roff, d_rlen, d_mask, d_rec, n}; }
+    BatchView view() const { return BatchView{d_seqs - seq_lo, d_qoff, d_qlen, d_roff, d_rlen, d_mask, d_rec, n}; }
     ListSet lists() const { return ListSet{d_idx, d_meta, d_meta + N_LISTS, d_meta + 2 * N_LISTS, d_meta + 3 * N_LISTS}; }
     int32_t* count2() const { return d_meta + 4 * N_LISTS; }
     int32_t* cursor2() const { return d_meta + 5 * N_LISTS; }
@@ -94,11 +129,14 @@ static bool scoring_supported(const ssw_scoring* s, std::string* why)
 extern "C" void ssw_batch_destroy(ssw_batch* b)
 {
     if (!b) return;
+    TraceTimer tt("batch_destroy");
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    cudaFree(b->d_seqs); cudaFree(b->d_qoff); cudaFree(b->d_roff); cudaFree(b->d_qlen); cudaFree(b->d_rlen);
-    cudaFree(b->d_mask); cudaFree(b->d_rec); cudaFree(b->d_idx); cudaFree(b->d_idx2); cudaFree(b->d_meta);
-    cudaFree(b->d_sscr[0]); cudaFree(b->d_sscr[1]); cudaFree(b->d_bscr); cudaFree(b->d_cigar); cudaFree(b->d_cigar_used);
+    cudaStream_t fs = b->stream;
+    dev_free(b->d_seqs, fs); dev_free(b->d_qoff, fs); dev_free(b->d_roff, fs); dev_free(b->d_qlen, fs); dev_free(b->d_rlen, fs);
+    dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_meta, fs);
+    dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
+    if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -108,72 +146,96 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
                        const int64_t* r_off, const int32_t* r_len, const int32_t* mask_len)
 {
     const int32_t n = b->n;
-    std::vector<int32_t> mask(n);
+    TraceTimer tt("batch_alloc (validate+alloc+h2d enqueue)");
+    b->h_mask.resize(n);
     memset(b->have, 0, sizeof b->have);
     int maxScore = 0;
     for (int k = 0; k < 25; ++k) maxScore = std::max<int>(maxScore, b->sc.mat[k]);
-    long long cig_cap = 16;
+    long long cig_worst = 16, q_total = 0;
+    long long lo = seqs_len, hi = 0;
     for (int32_t p = 0; p < n; ++p) {
         const int m = q_len[p], r = r_len[p];
         if (m < 0 || r < 0 || q_off[p] < 0 || r_off[p] < 0 || q_off[p] + m > seqs_len || r_off[p] + r > seqs_len) {
             set_error("pair " + std::to_string(p) + ": offsets/lengths outside the sequence buffer");
             return SSW_ERR_ARG;
         }
-        mask[p] = mask_len ? mask_len[p] : (m > 30 ? m / 2 : 15);          // ssw_wrap.py:196-199
+        b->h_mask[p] = mask_len ? mask_len[p] : (m > 30 ? m / 2 : 15);      // ssw_wrap.py:196-199
         b->max_q = std::max(b->max_q, m);
         b->max_r = std::max(b->max_r, r);
+        lo = std::min<long long>(lo, std::min(q_off[p], r_off[p]));
+        hi = std::max<long long>(hi, std::max(q_off[p] + m, r_off[p] + r));
         if (m > 0 && r > 0) {
             const int kind = (b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255) ? 1 : 0;
             const int K = strip_height_for(m, kind);
             b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
             b->maxK = std::max(b->maxK, std::max(K, strip_height_for(m, 0)));
-            cig_cap += 2LL * m + 3;
+            cig_worst += 2LL * m + 3;
+            q_total += m;
         }
     }
-    cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, b->device));
-    b->sms = prop.multiProcessorCount;
+    if (hi < lo) { lo = 0; hi = 0; }
+    b->seq_lo = lo; b->seq_hi = hi;
+    // Allocation sizes are functions of these three numbers; they are rounded up so that consecutive
+    // batches of similar shape request identical blocks and the stream-ordered pool can hand the same
+    // memory back instead of growing.
+    const int cap_q = (b->max_q + 255) & ~255, cap_r = (b->max_r + 255) & ~255;
+    const size_t cap_seq = ((size_t)(hi - lo) + (4u << 20)) & ~(size_t)((4u << 20) - 1);
+    CU_TRY(cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, b->device));
 
-    const size_t nn = (size_t)std::max(n, 1);
-    CU_TRY(cudaMalloc(&b->d_seqs, (size_t)std::max<int64_t>(seqs_len, 1)));
-    CU_TRY(cudaMalloc(&b->d_qoff, nn * 8)); CU_TRY(cudaMalloc(&b->d_roff, nn * 8));
-    CU_TRY(cudaMalloc(&b->d_qlen, nn * 4)); CU_TRY(cudaMalloc(&b->d_rlen, nn * 4)); CU_TRY(cudaMalloc(&b->d_mask, nn * 4));
-    CU_TRY(cudaMalloc(&b->d_rec, nn * sizeof(PairRec)));
-    CU_TRY(cudaMalloc(&b->d_idx, nn * 4)); CU_TRY(cudaMalloc(&b->d_idx2, nn * 4));
-    CU_TRY(cudaMalloc(&b->d_meta, 6 * N_LISTS * 4));
-    CU_TRY(cudaMalloc(&b->d_cigar_used, 8));
-    CU_TRY(cudaMemcpyAsync(b->d_seqs, seqs, (size_t)seqs_len, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_qoff, q_off, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_roff, r_off, (size_t)n * 8, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_qlen, q_len, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_rlen, r_len, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_mask, mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaStreamSynchronize(b->stream));       // `mask` is a local; the user buffers may be pageable
+    cudaStream_t st = b->stream;
+    const size_t nn = ((size_t)std::max(n, 1) + 16383) & ~(size_t)16383;
+    CU_TRY(dev_alloc_t(&b->d_qoff, nn, st)); CU_TRY(dev_alloc_t(&b->d_roff, nn, st));
+    CU_TRY(dev_alloc_t(&b->d_qlen, nn, st)); CU_TRY(dev_alloc_t(&b->d_rlen, nn, st)); CU_TRY(dev_alloc_t(&b->d_mask, nn, st));
+    CU_TRY(dev_alloc_t(&b->d_rec, nn, st));
+    CU_TRY(dev_alloc_t(&b->d_idx, nn, st)); CU_TRY(dev_alloc_t(&b->d_idx2, nn, st));
+    CU_TRY(dev_alloc_t(&b->d_meta, 6 * N_LISTS, st));
+    CU_TRY(dev_alloc_t(&b->d_cigar_used, 1, st));
+    CU_TRY(dev_alloc_t(&b->d_seqs, cap_seq, st));
+    CU_TRY(cudaMemcpyAsync(b->d_qoff, q_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b->d_roff, r_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b->d_qlen, q_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b->d_rlen, r_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b->d_mask, b->h_mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    // only the bytes the pairs of this batch reference travel; with pinned caller memory this copy is
+    // asynchronous (the caller keeps `seqs` alive until ssw_batch_fetch, like every CUDA async copy)
+    if (hi > lo) CU_TRY(cudaMemcpyAsync(b->d_seqs, seqs + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
 
     // score-pass scratch: class 0 = references up to LONG_REF_THRESHOLD columns, class 1 = longer ones
     for (int cls = 0; cls < 2; ++cls) {
         bool any = false;
         for (int kind = 0; kind < 2; ++kind) for (int K = 1; K <= KMAX; ++K) any |= b->have[cls][kind][K];
         if (!any) continue;
-        const int ncap = cls == 0 ? std::min(b->max_r, LONG_REF_THRESHOLD) : b->max_r;
+        const int ncap = cls == 0 ? std::min(cap_r, LONG_REF_THRESHOLD) : cap_r;
         b->sstride[cls] = score_scratch_layout(ncap, &b->off_col[cls], &b->off_bnd[cls], &b->off_snap[cls]);
         long long blocks = SCRATCH_BUDGET / (b->sstride[cls] * SCORE_WARPS);
         blocks = std::max<long long>(1, std::min<long long>(blocks, b->sms));
-        blocks = std::min<long long>(blocks, (n + SCORE_WARPS - 1) / SCORE_WARPS);
+        blocks = std::min<long long>(blocks, (n + 15) / 16);
         b->sblocks[cls] = (int)blocks;
-        CU_TRY(cudaMalloc(&b->d_sscr[cls], (size_t)(blocks * SCORE_WARPS * b->sstride[cls])));
+        CU_TRY(dev_alloc_t(&b->d_sscr[cls], (size_t)(blocks * SCORE_WARPS * b->sstride[cls]), st));
     }
     // CIGAR stage scratch and output
     if (b->sc.flag != 0) {
-        b->bstage = b->max_q + b->max_r + 16;
-        b->bdir = std::min<long long>(std::max<long long>(65536, 192LL * std::min(b->max_q, b->max_r + b->max_q)), 16LL << 20);
+        b->bstage = cap_q + cap_r + 16;
+        const long long rows = std::min(cap_q, cap_r + cap_q);           // rows of the trimmed rectangle <= query length
+        // narrow instance: row stride <= 128 bytes; wide instance: up to 1024 diagonals (wider bands, or
+        // longer reads, are re-run from ssw_batch_fetch with a scratch sized for them)
+        b->bdir = std::max<long long>(65536, 128LL * rows);
         b->bstride = ((long long)b->bstage * 4 + b->bdir + 255) & ~255LL;
         long long blocks = std::min<long long>((long long)b->sms * 4, (n + BAND_WARPS - 1) / BAND_WARPS);
         blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->bstride * BAND_WARPS)));
         b->bblocks = (int)blocks;
-        CU_TRY(cudaMalloc(&b->d_bscr, (size_t)(blocks * BAND_WARPS * b->bstride)));
-        b->cigar_cap = cig_cap;
-        CU_TRY(cudaMalloc(&b->d_cigar, (size_t)cig_cap * 4));
+        CU_TRY(dev_alloc_t(&b->d_bscr, (size_t)(blocks * BAND_WARPS * b->bstride), st));
+        b->wdir = std::min<long long>(1024LL * rows + 65536, 64LL << 20);
+        b->wstride = ((long long)b->bstage * 4 + b->wdir + 255) & ~255LL;
+        blocks = std::min<long long>((long long)b->sms * 2, (n + BAND_WARPS - 1) / BAND_WARPS);
+        blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->wstride * BAND_WARPS)));
+        b->wblocks = (int)blocks;
+        CU_TRY(dev_alloc_t(&b->d_wscr, (size_t)(blocks * BAND_WARPS * b->wstride), st));
+        // CIGAR output: the worst case is 2*len(query)+3 ops per pair; real alignments need a small
+        // fraction of that, so start with an estimate and grow to the worst case only if a run overflows
+        b->cigar_worst = cig_worst;
+        b->cigar_cap = std::min<long long>(cig_worst, (std::max<long long>(1 << 16, q_total / 2 + 16LL * n) + (1 << 20)) & ~((1LL << 20) - 1));
+        CU_TRY(dev_alloc_t(&b->d_cigar, (size_t)b->cigar_cap, st));
     }
     return SSW_OK;
 }
@@ -217,16 +279,41 @@ extern "C" ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs
     return b;
 }
 
+// CIGAR pass: list of pairs that pass the reference's gate (ssw.c:850), narrow instance, then the wide
+// instance for the pairs the narrow one handed over.
+static int enqueue_cigar_stage(ssw_batch* b, int* launches)
+{
+    cudaStream_t st = b->stream;
+    const BatchView view = b->view();
+    const ListSet ls = b->lists();
+    CU_TRY(cudaMemsetAsync(b->d_cigar_used, 0, 8, st));
+    CU_TRY(build_band_list(view, b->sc, ls, st, launches));
+    BandArgs ba;
+    ba.b = view; ba.sc = b->sc;
+    ba.wl = WorkList{ls.idx, nullptr, ls.count, ls.cursor};
+    ba.scratch = b->d_bscr; ba.scratch_stride = b->bstride; ba.dir_bytes = b->bdir;
+    ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap;
+    ba.cigar_used = b->d_cigar_used;
+    ba.next_idx = b->d_idx2; ba.next_count = b->count2();
+    CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
+    CU_TRY(launch_band(false, ba, b->bblocks, st));
+    ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+    ba.scratch = b->d_wscr; ba.scratch_stride = b->wstride; ba.dir_bytes = b->wdir;
+    CU_TRY(launch_band(true, ba, b->wblocks, st));
+    *launches += 2;
+    return SSW_OK;
+}
+
 extern "C" int ssw_batch_run(ssw_batch* b)
 {
     if (!b) return SSW_ERR_ARG;
     CU_TRY(cudaSetDevice(b->device));
     if (b->n == 0) return SSW_OK;
     cudaStream_t st = b->stream;
+    TraceTimer tt("batch_run (enqueue)");
     int launches = 0;
     const BatchView view = b->view();
     const ListSet ls = b->lists();
-    CU_TRY(cudaMemsetAsync(b->d_cigar_used, 0, 8, st));
     CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
 
     auto score_args = [&](int cls) {
@@ -283,19 +370,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         }
         CU_TRY(cudaEventRecord(b->ev[3], st));
         // ---- CIGAR pass
-        CU_TRY(build_band_list(view, b->sc, ls, st, &launches));
-        BandArgs ba;
-        ba.b = view; ba.sc = b->sc;
-        ba.wl = WorkList{ls.idx, nullptr, ls.count, ls.cursor};
-        ba.scratch = b->d_bscr; ba.scratch_stride = b->bstride; ba.dir_bytes = b->bdir;
-        ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap;
-        ba.cigar_used = b->d_cigar_used;
-        ba.next_idx = b->d_idx2; ba.next_count = b->count2(); 
-        CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
-        CU_TRY(launch_band(false, ba, b->bblocks, st));
-        ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
-        CU_TRY(launch_band(true, ba, b->bblocks, st));
-        launches += 2;
+        { const int rc = enqueue_cigar_stage(b, &launches); if (rc != SSW_OK) return rc; }
     }
     else CU_TRY(cudaEventRecord(b->ev[3], st));
     CU_TRY(cudaEventRecord(b->ev[4], st));
@@ -331,7 +406,7 @@ static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
     long long warps = std::max<long long>(1, std::min<long long>((6LL << 30) / stride, (long long)big.size()));
     const int blocks = (int)std::max<long long>(1, std::min<long long>((warps + BAND_WARPS - 1) / BAND_WARPS, b->sms));
     unsigned char* scr = nullptr;
-    CU_TRY(cudaMalloc(&scr, (size_t)(stride * blocks * BAND_WARPS)));
+    CU_TRY(dev_alloc_t(&scr, (size_t)(stride * blocks * BAND_WARPS), st));
     const ListSet ls = b->lists();
     const int32_t cnt = (int32_t)big.size();
     for (int32_t p : big) b->h_rec[p].status &= ~PS_BAND_SCRATCH;
@@ -356,7 +431,7 @@ static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
     for (int32_t p : big)
         CU_TRY(cudaMemcpyAsync(&b->h_rec[p], &b->d_rec[p], sizeof(PairRec), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    cudaFree(scr);
+    dev_free(scr, st);
     return SSW_OK;
 }
 
@@ -367,9 +442,12 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
     if (cigar_used) *cigar_used = 0;
     if (b->n == 0) return SSW_OK;
     cudaStream_t st = b->stream;
+    TraceTimer tt("batch_fetch (total)");
     b->h_rec.resize(b->n);
+    { TraceTimer t2("  fetch: wait for kernels"); CU_TRY(cudaStreamSynchronize(st)); }
+    { TraceTimer t2("  fetch: d2h records");
     CU_TRY(cudaMemcpyAsync(b->h_rec.data(), b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaStreamSynchronize(st)); }
     if (b->sc.flag != 0) {
         std::vector<int32_t> big;
         for (int32_t p = 0; p < b->n; ++p) if (b->h_rec[p].status & PS_BAND_SCRATCH) big.push_back(p);
@@ -379,10 +457,25 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
     if (b->sc.flag != 0) {
         CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        if ((long long)used > b->cigar_cap && b->cigar_cap < b->cigar_worst) {
+            // the estimated CIGAR buffer overflowed: grow it to the worst case and redo the CIGAR pass
+            dev_free(b->d_cigar, st);
+            b->d_cigar = nullptr;
+            b->cigar_cap = b->cigar_worst;
+            CU_TRY(dev_alloc_t(&b->d_cigar, (size_t)b->cigar_cap, st));
+            CU_TRY(clear_status_bits(b->view(), PS_CIGAR_CAP, st));
+            int launches = 1;
+            { const int rc = enqueue_cigar_stage(b, &launches); if (rc != SSW_OK) return rc; }
+            b->launches += launches;
+            CU_TRY(cudaMemcpyAsync(b->h_rec.data(), b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
         if (cigar_used) *cigar_used = (int64_t)used;
         if ((long long)used > b->cigar_cap) { set_error("internal cigar buffer exhausted"); return SSW_ERR_CIGAR_CAP; }
         if (used > 0) {
             if (!cigar_buf || (int64_t)used > cigar_cap) { set_error("cigar buffer too small"); return SSW_ERR_CIGAR_CAP; }
+            TraceTimer t2("  fetch: d2h cigars");
             CU_TRY(cudaMemcpyAsync(cigar_buf, b->d_cigar, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
         }
@@ -402,17 +495,60 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
     return SSW_OK;
 }
 
+static int error_code_of_create()
+{
+    return g_last_error.find("not supported") != std::string::npos ? SSW_ERR_UNSUPPORTED
+         : (g_last_error.find("no usable CUDA") != std::string::npos ? SSW_ERR_NODEVICE
+         : (g_last_error.find("cuda") != std::string::npos ? SSW_ERR_CUDA : SSW_ERR_ARG));
+}
+
+// One-shot call on host buffers.  Large batches are cut into chunks of SSW_CUDA_CHUNK pairs (default
+// 131072) that run as separate device batches on two alternating streams: the host-to-device copy of chunk
+// k+1 and the device-to-host copy of chunk k-1 overlap the kernels of chunk k (with pinned caller memory;
+// pageable memory still works, the copies then serialise).  Each chunk uploads only the byte range of
+// `seqs` its pairs reference, so a pair-major layout moves every byte once.
 extern "C" int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len, const int64_t* q_off,
                                const int32_t* q_len, const int64_t* r_off, const int32_t* r_len, const int32_t* mask_len,
                                const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap,
                                int64_t* cigar_used)
 {
-    ssw_batch* b = ssw_batch_create(device, nullptr, n_pairs, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len, scoring);
-    if (!b) return g_last_error.find("not supported") != std::string::npos ? SSW_ERR_UNSUPPORTED
-                 : (g_last_error.find("no usable CUDA") != std::string::npos ? SSW_ERR_NODEVICE : SSW_ERR_ARG);
-    int rc = ssw_batch_run(b);
-    if (rc == SSW_OK) rc = ssw_batch_fetch(b, out, cigar_buf, cigar_cap, cigar_used);
-    ssw_batch_destroy(b);
+    int32_t chunk = 131072;
+    if (const char* e = getenv("SSW_CUDA_CHUNK")) { const long v = atol(e); if (v > 0 && v < (1L << 30)) chunk = (int32_t)v; }
+    if (cigar_used) *cigar_used = 0;
+    if (n_pairs <= 0) return n_pairs == 0 ? SSW_OK : SSW_ERR_ARG;
+    ssw_batch* slot[2] = {nullptr, nullptr};
+    int32_t slot_p0[2] = {0, 0};
+    int64_t cig_base = 0;
+    int rc = SSW_OK;
+    auto finish = [&](int sidx) -> int {
+        ssw_batch* b = slot[sidx];
+        if (!b) return SSW_OK;
+        int64_t used = 0;
+        int r = ssw_batch_fetch(b, out + slot_p0[sidx], cigar_buf ? cigar_buf + cig_base : nullptr,
+                                cigar_buf ? cigar_cap - cig_base : 0, &used);
+        if (r == SSW_OK) {
+            for (int32_t p = 0; p < b->n; ++p) out[slot_p0[sidx] + p].cigar_off += cig_base;
+            cig_base += used;
+        } else if (r == SSW_ERR_CIGAR_CAP && cigar_used) *cigar_used = cig_base + used;
+        ssw_batch_destroy(b);
+        slot[sidx] = nullptr;
+        return r;
+    };
+    int k = 0;
+    for (int32_t p0 = 0; p0 < n_pairs && rc == SSW_OK; p0 += chunk, ++k) {
+        const int32_t cnt = std::min<int32_t>(chunk, n_pairs - p0);
+        const int sidx = k & 1;
+        ssw_batch* b = ssw_batch_create(device, nullptr, cnt, seqs, seqs_len, q_off + p0, q_len + p0, r_off + p0, r_len + p0,
+                                        mask_len ? mask_len + p0 : nullptr, scoring);
+        if (!b) { rc = error_code_of_create(); break; }
+        slot[sidx] = b; slot_p0[sidx] = p0;
+        rc = ssw_batch_run(b);
+        if (rc != SSW_OK) break;
+        rc = finish(sidx ^ 1);                      // the previous chunk: its kernels ran while this one was uploaded
+    }
+    if (rc == SSW_OK && k > 0) rc = finish((k - 1) & 1);       // the last chunk
+    for (int sidx = 0; sidx < 2; ++sidx) if (slot[sidx]) { ssw_batch_destroy(slot[sidx]); slot[sidx] = nullptr; }
+    if (rc == SSW_OK && cigar_used) *cigar_used = cig_base;
     return rc;
 }
 

@@ -6,8 +6,10 @@
 namespace sswb {
 
 constexpr int WARP = 32;
-constexpr int SCORE_WARPS = 16;                 // warps per CTA of the score-pass kernels (512 threads)
-constexpr int SCORE_THREADS = SCORE_WARPS * WARP;
+constexpr int SCORE_WARPS = 24;                 // most warps a CTA of the score-pass kernels can have (scratch is sized for it)
+// warps per CTA by strip height: fewer rows per strip need fewer registers, and the DPX dependency chains
+// want as many warps per scheduler as the register file allows (one CTA per SM: the LUT takes 80 KB)
+__host__ __device__ constexpr int score_warps(int K) { return K < 0 ? 24 : 16; }
 constexpr int VSTRIPS = 64;                     // virtual strips per warp: 32 lanes x 2 packed halves
 constexpr int KMAX = 16;                        // max query rows per strip -> 1024 rows per tile
 constexpr int LUT_ENTRIES = 625;                // (ref pair 25) x (query pair 25)

@@ -59,6 +59,9 @@ cudaError_t build_lists(int stage, const BatchView& b, const Scoring& sc, int lo
 // all pairs that still need the CIGAR pass, in one list (count at ls.count[0])
 cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet& ls, cudaStream_t st, int* launches);
 
+// clear status bits (and the CIGAR window) of every pair, e.g. before the CIGAR pass is repeated
+cudaError_t clear_status_bits(const BatchView& b, int bits, cudaStream_t st);
+
 // ---- banded DP + traceback (ssw_band.cu)
 struct BandArgs {
     BatchView b;

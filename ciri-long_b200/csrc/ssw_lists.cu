@@ -140,4 +140,16 @@ cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet
     return cudaGetLastError();
 }
 
+__global__ void clear_status_kernel(BatchView b, int bits)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.n_pairs) { b.rec[p].status &= ~bits; b.rec[p].cigar_len = 0; b.rec[p].cigar_off = 0; }
+}
+
+cudaError_t clear_status_bits(const BatchView& b, int bits, cudaStream_t st)
+{
+    clear_status_kernel<<<(b.n_pairs + 255) / 256, 256, 0, st>>>(b, bits);
+    return cudaGetLastError();
+}
+
 }  // namespace sswb

@@ -437,7 +437,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
 }
 
 template <int K, bool TRUNC, bool REV>
-__global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreArgs a)
+__global__ void __launch_bounds__(score_warps(K) * 32, 1) score_kernel(const ScoreArgs a)
 {
     extern __shared__ unsigned lut[];
     const int count = *a.wl.count;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreArgs
     const int warp = threadIdx.x >> 5;
     const int base = a.wl.base ? *a.wl.base : 0;
     unsigned char* rpw = reinterpret_cast<unsigned char*>(lut) + LUT_BYTES + warp * RP_WINDOW;
-    unsigned char* ws = a.scratch + (size_t)(blockIdx.x * SCORE_WARPS + warp) * a.scratch_stride;
+    unsigned char* ws = a.scratch + (size_t)(blockIdx.x * score_warps(K) + warp) * a.scratch_stride;
     for (;;) {
         int idx = 0;
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
@@ -479,7 +479,7 @@ static cudaError_t launch_one(const ScoreArgs& a, int blocks, cudaStream_t st)
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    score_kernel<K, TRUNC, REV><<<blocks, SCORE_THREADS, SCORE_SMEM_BYTES, st>>>(a);
+    score_kernel<K, TRUNC, REV><<<blocks, score_warps(K) * 32, SCORE_SMEM_BYTES, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,9 @@ def _load():
     lib.ssw_batch_stage_ms.argtypes = [c_void_p, c_void_p]
     lib.ssw_batch_destroy.restype = None
     lib.ssw_batch_destroy.argtypes = [c_void_p]
+    lib.ssw_align_batch.restype = c_int
+    lib.ssw_align_batch.argtypes = [c_int, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    POINTER(SSWScoring), c_void_p, c_void_p, c_int64, POINTER(c_int64)]
     lib.ssw_cuda_last_error.restype = c_char_p
     lib.ssw_cuda_device_count.restype = c_int
     lib.ssw_cuda_dpx_peak.restype = c_int
@@ -171,12 +174,15 @@ class DeviceBatch(object):
     def launch_count(self):
         return int(self.libssw.ssw_batch_launch_count(self.handle))
 
-    def fetch(self, cigar_cap=None):
-        """-> (records[RESULT_DTYPE], cigar uint32 array)"""
-        out = np.zeros(self.n, dtype=RESULT_DTYPE)
-        if cigar_cap is None:
-            cigar_cap = int(2 * self.q_len.astype(np.int64).sum() + 3 * self.n + 16) if self.flag else 1
-        cig = np.empty(cigar_cap, dtype=np.uint32)
+    def fetch(self, cigar_cap=None, out=None, cig=None):
+        """-> (records[RESULT_DTYPE], cigar uint32 array).  `out` / `cig` may be preallocated (e.g. pinned)."""
+        if out is None:
+            out = np.zeros(self.n, dtype=RESULT_DTYPE)
+        if cig is None:
+            if cigar_cap is None:
+                cigar_cap = int(2 * self.q_len.astype(np.int64).sum() + 3 * self.n + 16) if self.flag else 1
+            cig = np.empty(cigar_cap, dtype=np.uint32)
+        cigar_cap = len(cig)
         used = c_int64(0)
         rc = self.libssw.ssw_batch_fetch(self.handle, out.ctypes.data, cig.ctypes.data, cigar_cap, byref(used))
         if rc != 0:
@@ -447,6 +453,29 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
         else:
             out.append(None)
     return out
+
+
+def align_arrays(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend, flag=1, mask_len=None,
+                 device=0, out=None, cig=None):
+    """The one-shot C call (ssw_align_batch) on struct-of-arrays host buffers: upload, all kernels and
+    download in one call, chunk-pipelined inside the library.  Returns (records, cigar ops)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.int8)
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64); r_off = np.ascontiguousarray(r_off, dtype=np.int64)
+    q_len = np.ascontiguousarray(q_len, dtype=np.int32); r_len = np.ascontiguousarray(r_len, dtype=np.int32)
+    n = len(q_len)
+    if out is None:
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+    if cig is None:
+        cig = np.empty(int(2 * q_len.astype(np.int64).sum() + 3 * n + 16) if flag else 1, dtype=np.uint32)
+    sc = make_scoring(match, mismatch, gap_open, gap_extend, flag)
+    used = c_int64(0)
+    ml = None if mask_len is None else np.ascontiguousarray(mask_len, dtype=np.int32)
+    rc = Aligner.libssw.ssw_align_batch(device, n, seqs.ctypes.data, seqs.size, q_off.ctypes.data, q_len.ctypes.data,
+                                        r_off.ctypes.data, r_len.ctypes.data, None if ml is None else ml.ctypes.data,
+                                        byref(sc), out.ctypes.data, cig.ctypes.data, len(cig), byref(used))
+    if rc != 0:
+        raise SSWCudaError("ssw_align_batch: %d %s" % (rc, Aligner.libssw.ssw_cuda_last_error().decode()))
+    return out, cig[:used.value]
 
 
 def dpx_peak(device=0):

@@ -199,7 +199,7 @@ def from_lists(queries, refs, params, name="list"):
 
 
 def bsj_refinement_pairs_torch(n_pairs, device, seed=SEED_BASE + 2, ref_len=2000, q_min=300, q_max=800,
-                               n_frac=0.01, params=(1, 1, 1, 1), chunk=262144):
+                               n_frac=0.01, params=(1, 1, 1, 1), chunk=131072):
     """Config C2 generated on the GPU with torch (same recipe as bsj_refinement_pairs, different RNG
     stream): a million pairs take about a second instead of minutes.  Returns a PairBatch of numpy
     arrays (host)."""
@@ -242,10 +242,16 @@ def bsj_refinement_pairs_torch(n_pairs, device, seed=SEED_BASE + 2, ref_len=2000
         del refs, codes, new, u, reps, pos, inserted, rnd, src, base, seg_id
     q_len = np.concatenate(qlens)
     r_len = np.full(n_pairs, ref_len, dtype=np.int32)
-    # layout: all queries, then all references (offsets are explicit, so any layout is legal)
-    q_codes = np.concatenate(parts_q)
-    r_codes = np.concatenate(parts_r)
-    q_off = (np.cumsum(q_len.astype(np.int64)) - q_len).astype(np.int64)
-    r_off = (len(q_codes) + np.arange(n_pairs, dtype=np.int64) * ref_len).astype(np.int64)
-    seqs = np.concatenate([q_codes, r_codes])
+    # layout: per generation chunk [queries of the chunk][references of the chunk], so that consecutive
+    # pairs reference a compact byte range (the one-shot C call uploads chunk by chunk)
+    blocks, q_off, r_off, pos, p0 = [], np.empty(n_pairs, np.int64), np.empty(n_pairs, np.int64), 0, 0
+    for qc, rc, ql in zip(parts_q, parts_r, qlens):
+        k = len(ql)
+        q_off[p0:p0 + k] = pos + np.cumsum(ql.astype(np.int64)) - ql
+        pos += len(qc)
+        r_off[p0:p0 + k] = pos + np.arange(k, dtype=np.int64) * ref_len
+        pos += len(rc)
+        blocks += [qc, rc]
+        p0 += k
+    seqs = np.concatenate(blocks)
     return PairBatch(seqs, q_off, q_len, r_off, r_len, *params, name="C2-bsj-refinement")

@@ -167,3 +167,22 @@ def test_wrapper_drop_in(sw, golden):
     ref0 = [sw.Aligner(same[0]["ref"], *p).align(c["query"]) for c in same[:5]]
     for a, b_ in zip(out[:5], ref0):
         assert (a.score, a.ref_begin, a.query_end) == (b_.score, b_.ref_begin, b_.query_end) and a.cigar_string is None
+
+
+def test_one_shot_chunked_call(sw, oracle, monkeypatch):
+    """ssw_align_batch cuts large batches into chunks on alternating streams: same results as one resident batch"""
+    from ciri_long_b200 import workloads as W
+    b = W.bsj_refinement_pairs(700, seed=31)
+    rec, cig = run_batch(sw, b)
+    monkeypatch.setenv("SSW_CUDA_CHUNK", "128")
+    r2, c2 = sw.align_arrays(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, b.match, b.mismatch, b.gap_open, b.gap_extend)
+    for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len", "status"):
+        assert (rec[k] == r2[k]).all(), k
+    for i in range(len(b)):
+        a = cig[rec["cigar_off"][i]:rec["cigar_off"][i] + rec["cigar_len"][i]]
+        c = c2[r2["cigar_off"][i]:r2["cigar_off"][i] + r2["cigar_len"][i]]
+        assert (a == c).all()
+    assert len(c2) == len(cig)
+    # a too small caller buffer is reported, not overrun
+    with pytest.raises(sw.SSWCudaError):
+        sw.align_arrays(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, 1, 1, 1, 1, cig=np.empty(10, np.uint32))
