@@ -175,7 +175,13 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
 
     int candM = 0, candCol = -1, candRow = 0;
     int termCol = -1, overCol = 0x7fffffff;
+    // Reverse pass only: if a cell above score1 turns up at or before the stop column (the two truncated-F
+    // passes disagree), the pass is repeated in exact mode: limited to the columns the reference visits
+    // (ssw.c:296,499 break) and with plain best-cell tracking.
+    bool exactMode = false;
 
+    for (int attempt = 0; attempt < (REV ? 2 : 1); ++attempt) {
+    candM = 0; candCol = -1; candRow = 0; termCol = -1; overCol = 0x7fffffff;
     for (int p = 0; p < T; ++p) {
         const bool lastTile = (p == T - 1);
         const StripGeom sLo = strip_geom<K, TRUNC>(p * VSTRIPS + lane, Vtot, dead, segLen, G, base, extra);
@@ -276,7 +282,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             }
             if (TRUNC) mxv &= stripMask;
             R = max_relu(rR, mxv);
-            if (REV) {
+            if (REV && !exactMode) {
                 // The reference stops at the first column whose maximum equals score1 (ssw.c:296,499), so
                 // cells above score1 only count if they occur before that column.  Strips ahead of the
                 // stop column keep running here: values above score1 are kept out of the best-cell
@@ -312,7 +318,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 if (colOk) wbnd[s] = make_uint2(__byte_perm(Hout, Fout, 0x7632u), R >> 16);   // always strip 63: high halves
             } else if (!REV) {
                 if (colOk) wcol[s] = wval;
-            } else if (colOk && !termflag && (int)(wval & 0xffffu) == terminate + go) {
+            } else if (colOk && !termflag && !exactMode && (int)(wval & 0xffffu) == terminate + go) {
                 termflag = 1; termCol = wHalf ? cHi : cLo;
             }
             ++cLo; ++cHi;
@@ -383,6 +389,16 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         if (lastTile) termCol = __shfl_sync(FULL, termCol, wLane);
         __syncwarp();      // boundary array / snapshots written by this tile are read by the next one
     }
+    if (REV && !exactMode) {
+        overCol = __reduce_min_sync(FULL, overCol);
+        if (overCol != 0x7fffffff && (termCol < 0 || overCol <= termCol)) {
+            exactMode = true;
+            if (termCol >= 0) n = termCol + 1;
+            continue;
+        }
+    }
+    break;
+    }
 
     if (!REV) {
         const bool over8 = candM + a.sc.bias >= 255;               // ssw.c:285,317
@@ -423,10 +439,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         }
     } else {
         int status = 0;
-        // a cell above score1 before the stop column (or with no stop column at all): the truncated-F
-        // flavour scored the prefix higher than the forward pass did; the exact kernel decides
-        overCol = __reduce_min_sync(FULL, overCol);
-        if (overCol != 0x7fffffff && (termCol < 0 || overCol <= termCol)) status |= PS_PUNT;
+        if (candM >= (TRUNC ? TRUNC_SCORE_LIMIT : S16_SCORE_LIMIT) - go) status |= PS_PUNT;
         if (lane == 0) {
             const int word = rec->word;
             rec->ref_begin1 = candM > 0 ? rec->ref_end1 - candCol : (word ? 0 : -1);

@@ -117,6 +117,14 @@ def fuzz_cases(rng):
             r = np.concatenate([rng.integers(0, 4, size=25).astype(np.int8), core,
                                 filler[:max(gap - L, 0)], second, rng.integers(0, 4, size=25).astype(np.int8)])
             cases.append(dict(name="rep_%d_%d_%d_%d_L%d_d%+d" % (p + (L, d)), params=p, ref=to_str(r), query=to_str(q)))
+    # gap_open == gap_extend with match != mismatch: the reverse pass can jump over score1 without ever
+    # equalling it (the stop rule of ssw.c:499 then fires late or never)
+    for p in ((3, 2, 2, 2), (2, 1, 1, 1)):
+        for t in range(30):
+            n = int(rng.integers(300, 600))
+            r = rng.integers(0, 4, size=n).astype(np.int8)
+            q = channel(r, .04, .06, .10, 6, rng)
+            cases.append(dict(name="revjump_%d_%d_%d_%d_%02d" % (p + (t,)), params=p, ref=to_str(r), query=to_str(q)))
     # hand-written vectors of SURVEY 8(c): G5 (score 0 / UB), G6 (N and unknown symbols), G7 (trap 3)
     cases.append(dict(name="G5_zero_score", params=(1, 1, 1, 1), ref="A" * 20, query="C" * 24))
     cases.append(dict(name="G6_n_and_unknown", params=(1, 1, 1, 1), ref="ACGTNNNNACGTACGTXX", query="ACGTACGTACGTACGTRY"))
