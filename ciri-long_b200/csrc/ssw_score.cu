@@ -207,6 +207,10 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         const int wLane = wv & 31, wHalf = wv >> 5;
 
         unsigned Hout = GO, Fout = GO, R = 0, diagIn = GO, best = GO;
+        // best  = per strip, the largest H recorded with its column and a snapshot of the strip's H column
+        // bestT = max(best, the largest H any strip of this warp has recorded, refreshed every 32 steps):
+        //         a cell below that can never be the pair's maximum, so it is not recorded at all
+        unsigned bestT = GO;
         int bcolLo = -1, bcolHi = -1;
         int cLo = -lane, cHi = -lane - 32;
         int termflag = 0;
@@ -296,19 +300,21 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 }
             }
             bool pHi, pLo;
-            const unsigned nb = __vibmax_s16x2(best, mxv, &pHi, &pLo);   // pred = (best >= mxv)
+            const unsigned nb = __vibmax_s16x2(bestT, mxv, &pHi, &pLo);  // pred = (bestT >= mxv)
             if (!(pHi && pLo)) {
                 if (!pLo) {
+                    best = (best & 0xffff0000u) | (mxv & 0xffffu);
                     bcolLo = cLo;
 #pragma unroll
                     for (int i = 0; i < K; ++i) snap[i * 32 + lane] = Hd[i];
                 }
                 if (!pHi) {
+                    best = (best & 0xffffu) | (mxv & 0xffff0000u);
                     bcolHi = cHi;
 #pragma unroll
                     for (int i = 0; i < K; ++i) snap[(K + i) * 32 + lane] = Hd[i];
                 }
-                best = nb;
+                bestT = nb;
             }
             // the complete column leaves the tile at the writer strip
             const unsigned wval = __byte_perm(R, Hout, selW);               // colmax | H(last row) << 16 of the writer's half
@@ -329,6 +335,11 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         // Chunk borders fall on the phase borders: pipeline fill [0, 63), steady state [63, n), drain [n, steps).
         const int sA = steps < 63 ? steps : 63;
         int sB = n < steps ? n : steps; if (sB < sA) sB = sA;
+        auto refresh = [&]() {
+            const int lo = lo16(best), hi = hi16(best);
+            const int g = __reduce_max_sync(FULL, lo > hi ? lo : hi);
+            bestT = max_relu(bestT, pack2(g, g));
+        };
         auto sweep = [&](auto top) {
             int s0 = 0;
             bool stop = false;
@@ -353,6 +364,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                     for (int t = 0; t < len; ++t) {
                         step(std::false_type{}, top, s0 + t, t);
                         if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
+                        if ((t & 31) == 31) refresh();
                     }
                 } else {
                     for (int t = 0; t < len; ++t) {
