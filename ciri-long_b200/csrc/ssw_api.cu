@@ -82,7 +82,7 @@ struct ssw_batch {
     int32_t *d_qlen = nullptr, *d_rlen = nullptr, *d_mask = nullptr;
     PairRec* d_rec = nullptr;
     // lists: [count | base | fill | cursor | count2 | cursor2] x N_LISTS
-    int32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_meta = nullptr;
+    int32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_idx3 = nullptr, *d_meta = nullptr;
     // scratch
     unsigned char* d_sscr[2] = {nullptr, nullptr};
     long long sstride[2] = {0, 0}, off_col[2] = {0, 0}, off_bnd[2] = {0, 0}, off_snap[2] = {0, 0};
@@ -134,7 +134,7 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaStream_t fs = b->stream;
     dev_free(b->d_seqs, fs); dev_free(b->d_qoff, fs); dev_free(b->d_roff, fs); dev_free(b->d_qlen, fs); dev_free(b->d_rlen, fs);
-    dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_meta, fs);
+    dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_meta, fs);
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
@@ -187,7 +187,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     CU_TRY(dev_alloc_t(&b->d_qoff, nn, st)); CU_TRY(dev_alloc_t(&b->d_roff, nn, st));
     CU_TRY(dev_alloc_t(&b->d_qlen, nn, st)); CU_TRY(dev_alloc_t(&b->d_rlen, nn, st)); CU_TRY(dev_alloc_t(&b->d_mask, nn, st));
     CU_TRY(dev_alloc_t(&b->d_rec, nn, st));
-    CU_TRY(dev_alloc_t(&b->d_idx, nn, st)); CU_TRY(dev_alloc_t(&b->d_idx2, nn, st));
+    CU_TRY(dev_alloc_t(&b->d_idx, nn, st)); CU_TRY(dev_alloc_t(&b->d_idx2, nn, st)); CU_TRY(dev_alloc_t(&b->d_idx3, 2 * nn, st));
     CU_TRY(dev_alloc_t(&b->d_meta, 6 * N_LISTS, st));
     CU_TRY(dev_alloc_t(&b->d_cigar_used, 1, st));
     CU_TRY(dev_alloc_t(&b->d_seqs, cap_seq, st));
@@ -315,6 +315,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
     const BatchView view = b->view();
     const ListSet ls = b->lists();
     CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
+    const size_t nn3 = ((size_t)std::max(b->n, 1) + 16383) & ~(size_t)16383;       // stride of the two hand-over lists in d_idx3
 
     auto score_args = [&](int cls) {
         ScoreArgs a;
@@ -322,6 +323,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         a.scratch = b->d_sscr[cls]; a.scratch_stride = b->sstride[cls];
         a.off_col = b->off_col[cls]; a.off_bnd = b->off_bnd[cls]; a.off_snap = b->off_snap[cls];
         a.rerun = 0; a.next_idx = nullptr; a.next_base = nullptr; a.next_count = nullptr;
+        a.wide_idx = nullptr; a.wide_count = nullptr;
         return a;
     };
 
@@ -336,6 +338,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                 ScoreArgs a = score_args(cls);
                 a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
                 if (kind == 1) { a.next_idx = b->d_idx2; a.next_base = ls.base + id; a.next_count = b->count2() + id; }
+                a.wide_idx = b->d_idx3 + (size_t)kind * nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + kind;
                 CU_TRY(launch_score(K, kind == 1, false, a, b->sblocks[cls], st));
                 ++launches;
             }
@@ -351,6 +354,14 @@ extern "C" int ssw_batch_run(ssw_batch* b)
             CU_TRY(launch_score(K, false, false, a, b->sblocks[cls], st));
             ++launches;
         }
+    // ---- pairs whose score left the 16-bit comfort zone: 32-bit kernels (rare)
+    const int wcls = b->d_sscr[1] ? 1 : 0;
+    for (int kind = 0; kind < 2; ++kind) {
+        ScoreArgs a = score_args(wcls);
+        a.wl = WorkList{b->d_idx3 + (size_t)kind * nn3, nullptr, b->count2() + LIST_WIDE32 + 2 + kind, b->cursor2() + LIST_WIDE32 + 2 + kind};
+        CU_TRY(launch_score32(kind == 1, false, a, b->sblocks[wcls], st));
+        ++launches;
+    }
     CU_TRY(cudaEventRecord(b->ev[2], st));
     if (b->sc.flag != 0) {
         // ---- reverse pass: strip height follows the read prefix, so any K up to the forward maximum can occur
@@ -367,6 +378,13 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                     ++launches;
                 }
             }
+        }
+        for (int kind = 0; kind < 2; ++kind) {
+            const int id = LIST_WIDE32 + kind;
+            ScoreArgs a = score_args(wcls);
+            a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
+            CU_TRY(launch_score32(kind == 1, true, a, b->sblocks[wcls], st));
+            ++launches;
         }
         CU_TRY(cudaEventRecord(b->ev[3], st));
         // ---- CIGAR pass

@@ -10,6 +10,7 @@ constexpr int SCORE_WARPS = 24;                 // most warps a CTA of the score
 // warps per CTA by strip height: fewer rows per strip need fewer registers, and the DPX dependency chains
 // want as many warps per scheduler as the register file allows (one CTA per SM: the LUT takes 80 KB)
 __host__ __device__ constexpr int score_warps(int K) { return K < 0 ? 24 : 16; }
+constexpr int SCORE32_WARPS = 8;                // warps per CTA of the 32-bit score kernels
 constexpr int VSTRIPS = 64;                     // virtual strips per warp: 32 lanes x 2 packed halves
 constexpr int KMAX = 16;                        // max query rows per strip -> 1024 rows per tile
 constexpr int LUT_ENTRIES = 625;                // (ref pair 25) x (query pair 25)
@@ -30,7 +31,8 @@ enum : int32_t {
     PS_TRACEBACK_ERR = 4,   // traceback left the band / undefined direction (reference returns NULL)
     PS_BAND_SCRATCH = 8,    // direction matrix did not fit the per-warp scratch
     PS_CIGAR_CAP = 16,      // cigar output buffer exhausted
-    PS_UNSUPPORTED = 32
+    PS_UNSUPPORTED = 32,
+    PS_WIDE32 = 64          // scores near the 16-bit range: handled by the 32-bit score kernels
 };
 
 // one record per pair, device resident (mirrors ssw_result + internals)

@@ -16,6 +16,8 @@ struct ScoreArgs {
     int32_t* next_idx;             // TRUNC forward only: list of pairs that need the deciding GOTOH pass
     const int32_t* next_base;      //   (same partitioning as the forward lists)
     int32_t* next_count;
+    int32_t* wide_idx;             // forward only: pairs handed to the 32-bit kernels (ssw_score32.cu)
+    int32_t* wide_count;
 };
 
 // bytes of scratch one warp needs for references of up to n_cap columns
@@ -31,6 +33,8 @@ inline long long score_scratch_layout(int n_cap, long long* off_col, long long* 
 
 cudaError_t launch_score(int K, bool trunc, bool rev, const ScoreArgs& a, int blocks, cudaStream_t st);
 
+cudaError_t launch_score32(bool trunc, bool rev, const ScoreArgs& a, int blocks, cudaStream_t st);
+
 // strip height (template parameter K of the score kernel) for a query of m rows; must match ssw_score.cu
 __host__ __device__ inline int strip_height_for(int m, int trunc)
 {
@@ -42,7 +46,8 @@ __host__ __device__ inline int strip_height_for(int m, int trunc)
 
 // ---- work-list construction (ssw_lists.cu)
 // list id = cls * 34 + kind * 17 + K   (cls: 0 normal / 1 long reference; kind: 0 GOTOH / 1 TRUNC; K: 1..16)
-constexpr int N_LISTS = 2 * 2 * 17;
+constexpr int N_LISTS = 2 * 2 * 17 + 4;           // + 68/69: reverse lists of the 32-bit kernels; 70/71: their forward counters
+constexpr int LIST_WIDE32 = 68;
 __host__ __device__ inline int list_id(int cls, int kind, int K) { return cls * 34 + kind * 17 + K; }
 
 struct ListSet {

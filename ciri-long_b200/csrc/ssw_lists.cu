@@ -29,6 +29,7 @@ __device__ int classify(int stage, const BatchView& b, const Scoring& sc, int lo
     const int m = rec->read_end1 + 1, n = rec->ref_end1 + 1;
     if (n <= 0) return -2;          // score 0: nothing to walk (handled inline by the caller)
     const int kind = (rec->word && sc.go == sc.ge) ? 1 : 0;
+    if (rec->status & PS_WIDE32) return LIST_WIDE32 + kind;
     // the scratch class follows the full reference length (as in the forward pass), not the trimmed one
     return list_id(b.r_len[p] > long_thr ? 1 : 0, kind, strip_height(m, kind));
 }

@@ -444,7 +444,7 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
     out = []
     for i in range(len(queries)):
         r = rec[i]
-        if r['status'] != 0:
+        if (r['status'] & 0xff) != 0:
             out.append(None)
             continue
         match_len = r['read_end1'] - r['read_begin1'] + 1
