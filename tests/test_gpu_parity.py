@@ -200,3 +200,45 @@ def test_scores_beyond_16_bit_comfort(sw, oracle):
     check_batch(sw, oracle, W.square_pairs(2, 4096, params=(10, 4, 8, 2)))
     # gap_open == gap_extend: scores above 16000 leave the packed truncated-F kernel
     check_batch(sw, oracle, W.square_pairs(1, 8400, params=(2, 2, 2, 2), noise=False))
+
+
+def test_batched_call_sites(sw, oracle):
+    """callsites.py: the two-phase versions of find_bsj.align_clip_segments / collapse.junc_score give what
+    a per-pair loop through the drop-in Aligner gives"""
+    from ciri_long_b200 import callsites as cs
+    rng = np.random.default_rng(77)
+    bases = np.array(list("ACGT"))
+    genome = "".join(bases[rng.integers(0, 4, 6000)])
+    items = []
+    for k in range(24):
+        a = int(rng.integers(500, 4000)); L = int(rng.integers(300, 700))
+        circ_src = genome[a:a + L]
+        cut = int(rng.integers(30, 120))
+        circ = circ_src[cut:] + circ_src[:cut]                    # rotated: the tail of the read maps before its head
+        strand = 1 if k % 3 else -1
+        if strand < 0:
+            circ = cs.revcomp(circ)
+        q_st, q_en = (0, L - cut) if k % 2 else (5, L - cut)
+        hit = cs.Hit(q_st, q_en, a + cut, a + L, strand)
+        tmp_start, tmp_end = max(hit.r_st - 2000, 0), min(hit.r_en + 2000, len(genome))
+        items.append((circ, hit, genome[tmp_start:tmp_end], tmp_start, tmp_end))
+    items.append(("ACGTACGTACGTACGTACGTAAAA", cs.Hit(2, 20, 100, 118, 1), None, 0, 0))     # < 20 clipped bases: no alignment
+    got = cs.align_clip_segments_batch(items)
+    for it, g in zip(items, got):
+        assert g == cs.align_clip_segments_batch([it])[0]
+    # one item by hand, through the per-call drop-in
+    circ, hit, window, tmp_start, tmp_end = items[1]
+    clip_seq = circ[hit.q_en:] + circ[:hit.q_st]
+    res = sw.Aligner(window if hit.strand > 0 else cs.revcomp(window), 1, 1, 1, 1).align(clip_seq)
+    if hit.strand > 0:
+        exp = (tmp_start + res.ref_begin, tmp_start + res.ref_end)
+    else:
+        exp = (tmp_end - res.ref_end, tmp_end - res.ref_begin)
+    assert got[1][3][:2] == exp
+    assert got[-1] == ("GTACGTACGTACGTACGTAAAAAC", 99, 118, (None, None, 6))
+    spans = [genome[100:400], genome[1000:1200]]
+    reads = [[genome[380:400] + genome[100:130], genome[385:400] + genome[100:140]], [genome[1180:1200] + genome[1000:1030]]]
+    sc = cs.junc_score_batch(spans, reads)
+    for span, rs, s in zip(spans, reads, sc):
+        al = sw.Aligner(span * 2, 10, 4, 8, 2)
+        assert abs(s - np.mean([al.align(r).score for r in rs])) < 1e-9
