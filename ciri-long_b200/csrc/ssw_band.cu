@@ -22,6 +22,7 @@
 // which F is an exclusive max-plus prefix scan over the lanes.
 // Tie rules, the "stop at read row 0" rule and the zeroed vertical neighbour of the last column in the
 // first w+1 rows (ssw.c:595-596) are reproduced; see oracle/ssw_oracle.c:orc_band_cigar.
+#include <type_traits>
 #include "ssw_common.cuh"
 #include "ssw_kernels.h"
 
@@ -75,33 +76,46 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
     int jFirst = -lane + kkBase - bw;                           // column of my first diagonal in row i
     const int8_t* nextRef = ref + jFirst + DPL;                 // base entering my last diagonal in the next row
     unsigned char* drow = dir + (long long)i * rowStride + kkBase;
-    for (int r = 0; r < iters; ++r) {
-        const bool rowOk = (unsigned)i < (unsigned)readLen;
+    // lane-constant part of cell validity: diagonal inside the band (0/1, applied by multiplication so
+    // that it runs on the FMA pipe in the interior iterations)
+    int vd[DPL];
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) vd[d] = kkBase + d <= 2 * bw ? 1 : 0;
+
+    // One iteration.  INTERIOR = every lane that owns an in-band diagonal is on a row whose band lies fully
+    // inside the rectangle: validity is the lane constant vd[], the clipping rule of ssw.c:595-596 cannot apply.
+    auto iteration = [&](auto interior) {
+        constexpr bool INTERIOR = decltype(interior)::value;
+        const bool rowOk = INTERIOR || (unsigned)i < (unsigned)readLen;
         // left neighbour of my block: lane-1's last cell of the same row (computed one iteration ago)
         int Hl = __shfl_up_sync(FULL, lastH, 1), Fl = __shfl_up_sync(FULL, lastF, 1);
         if (lane == 0) { Hl = 0; Fl = 0; }
         unsigned rd = 4;
-        if (rowOk) { rd = (unsigned)read[i]; if (rd > 4u) rd = 4; }
+        if (INTERIOR) { if (vd[0]) { rd = (unsigned)read[i]; if (rd > 4u) rd = 4; } }
+        else if (rowOk) { rd = (unsigned)read[i]; if (rd > 4u) rd = 4; }
         const uint2 srow = stab[rd];
-        // columns of this row inside band and rectangle: beg <= j <= end  <=>  (unsigned)(j - beg) <= span
-        const int beg = i - bw > 0 ? i - bw : 0;
-        const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
-        const bool rowHas = rowOk && end >= beg;                 // rows past the band's reach hold no cell
-        const int span = rowHas ? end - beg : 0;
-        const int jrel = rowHas ? jFirst - beg : -(1 << 30);      // (unsigned) of a negative never passes the test
-        const bool quirk = QUIRK && i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;
-        const int jq = refLen - 1 - jFirst;                     // diagonal slot that sits on the last column
+        int span = 0, jrel = 0, jq = 0;
+        bool quirk = false;
+        if (!INTERIOR) {
+            // columns of this row inside band and rectangle: beg <= j <= end  <=>  (unsigned)(j - beg) <= span
+            const int beg = i - bw > 0 ? i - bw : 0;
+            const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
+            const bool rowHas = rowOk && end >= beg;             // rows past the band's reach hold no cell
+            span = rowHas ? end - beg : 0;
+            jrel = rowHas ? jFirst - beg : -(1 << 30);           // (unsigned) of a negative never passes the test
+            quirk = QUIRK && i >= 1 && i - 1 - bw <= 0 && i - 1 + bw >= refLen - 1;
+            jq = refLen - 1 - jFirst;                            // diagonal slot that sits on the last column
+        }
         unsigned dirw[(DPL + 3) / 4];
 #pragma unroll
         for (int w = 0; w < (DPL + 3) / 4; ++w) dirw[w] = 0;
         int upH = 0, upE = 0;                                   // (i-1, first diagonal of lane+1), known after d == 0
 #pragma unroll
         for (int d = 0; d < DPL; ++d) {
-            const bool valid = (unsigned)(jrel + d) <= (unsigned)span;
             int Hu, Eu;
             if (d + 1 < DPL) { Hu = Hp[d + 1]; Eu = Ep[d + 1]; }
             else { Hu = upH; Eu = upE; }
-            if (QUIRK) { if (quirk && d == jq) { Hu = 0; Eu = 0; } }
+            if (QUIRK && !INTERIOR) { if (quirk && d == jq) { Hu = 0; Eu = 0; } }
             const int s = (int)prmt_raw(srow.x, srow.y, sel[d]);
             const int eopen = Hu - go, eext = Eu - ge;
             const int E = eopen > eext ? eopen : eext;
@@ -114,7 +128,8 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
             unsigned code = (eopen > eext ? 1u : 0u) | (fopen > fext ? 2u : 0u);
             if (gapbest > dg) code |= e1 > f1 ? 4u : 8u;
             int Eo = E, Fo = F;
-            if (!valid) { H = 0; Eo = 0; Fo = 0; }
+            if (INTERIOR) { H *= vd[d]; Eo *= vd[d]; Fo *= vd[d]; }
+            else if (!((unsigned)(jrel + d) <= (unsigned)span)) { H = 0; Eo = 0; Fo = 0; }
             maxv = H > maxv ? H : maxv;
             dirw[d >> 2] |= code << (8 * (d & 3));
             Hp[d] = H; Ep[d] = Eo;
@@ -128,7 +143,7 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
             }
         }
         lastH = Hl; lastF = Fl;
-        if (rowOk) {
+        if (INTERIOR ? vd[0] != 0 : rowOk) {
             if (DPL == 2) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)dirw[0];
             else if (DPL == 4) *reinterpret_cast<unsigned*>(drow) = dirw[0];
             else if (DPL == 8) *reinterpret_cast<uint2*>(drow) = make_uint2(dirw[0], dirw[1]);
@@ -148,7 +163,18 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
             sel[DPL - 1] = c * 0x1111u + 0x8880u;
         }
         ++i; ++jFirst; ++nextRef; drow += rowStride;
-    }
+    };
+
+    // iterations [rA, rB) are interior for every lane that owns in-band diagonals (lanes 0 .. lmax)
+    const int lmax = (2 * bw) / DPL;
+    int rA = bw + lmax, rB = (readLen - 1 < refLen - 1 - bw ? readLen - 1 : refLen - 1 - bw) + 1;
+    if (rA > iters) rA = iters;
+    if (rB < rA) rB = rA;
+    if (rB > iters) rB = iters;
+    int r = 0;
+    for (; r < rA; ++r) iteration(std::false_type{});
+    for (; r < rB; ++r) iteration(std::true_type{});
+    for (; r < iters; ++r) iteration(std::false_type{});
     return __reduce_max_sync(FULL, maxv);
 }
 
