@@ -117,16 +117,18 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
             else { Hu = upH; Eu = upE; }
             if (QUIRK && !INTERIOR) { if (quirk && d == jq) { Hu = 0; Eu = 0; } }
             const int s = (int)prmt_raw(srow.x, srow.y, sel[d]);
+            // each max also delivers the comparison the direction code needs (VIMNMX with predicate output)
             const int eopen = Hu - go, eext = Eu - ge;
-            const int E = eopen > eext ? eopen : eext;
+            bool eExtWins, fExtWins, fWins, diagWins;
+            const int E = __vibmax_s32(eext, eopen, &eExtWins);            // eExtWins = (eext >= eopen): open only if strictly greater
             const int fopen = Hl - go, fext = Fl - ge;
-            const int F = fopen > fext ? fopen : fext;
+            const int F = __vibmax_s32(fext, fopen, &fExtWins);
             const int e1 = E > 0 ? E : 0, f1 = F > 0 ? F : 0;
-            const int gapbest = e1 > f1 ? e1 : f1;
+            const int gapbest = __vibmax_s32(f1, e1, &fWins);               // fWins = (f1 >= e1): E only if strictly greater
             const int dg = Hp[d] + s;
-            int H = gapbest > dg ? gapbest : dg;
-            unsigned code = (eopen > eext ? 1u : 0u) | (fopen > fext ? 2u : 0u);
-            if (gapbest > dg) code |= e1 > f1 ? 4u : 8u;
+            int H = __vibmax_s32(dg, gapbest, &diagWins);                   // diagWins = (dg >= gapbest)
+            unsigned code = (eExtWins ? 0u : 1u) | (fExtWins ? 0u : 2u);
+            if (!diagWins) code |= fWins ? 8u : 4u;
             int Eo = E, Fo = F;
             if (INTERIOR) { H *= vd[d]; Eo *= vd[d]; Fo *= vd[d]; }
             else if (!((unsigned)(jrel + d) <= (unsigned)span)) { H = 0; Eo = 0; Fo = 0; }
