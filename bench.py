@@ -272,6 +272,14 @@ def run_ours(args, rank, world, local_rank):
             peaks = json.load(f)
     except Exception:
         pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        # ncu dram bytes of the forward launches of one run, scaled to this run's pair count
+        traffic = tj["forward_dram_bytes_per_step"] * len(batch) / tj["pairs"]
+    except Exception:
+        pass
     fwd_ms = float(stage[0])
     fwd_gcups = cells / (fwd_ms * 1e-3) / 1e9
     peak_gcups = peak_lane / 3.0 / 1e9
@@ -291,7 +299,10 @@ def run_ours(args, rank, world, local_rank):
                              % (n_chk, "reference libssw.so" if O.RefLib.available() else "oracle port", n_bad_status)},
         "stage_ms": {"forward": fwd_ms, "deciding": float(stage[1]), "reverse": float(stage[2]), "cigar": float(stage[3])},
         "roofline": {"bound": "dpx", "achieved": fwd_gcups, "peak": peak_gcups, "unit": "GCUPS",
-                     "frac": fwd_gcups / peak_gcups, "traffic": None,
+                     "frac": fwd_gcups / peak_gcups, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step, from the "
+                                     "committed ncu capture profiles/r1_final_launches_1M.csv (bytes); algorithmic input is "
+                                     "%.2e bytes per step: the pass is DPX-bound, DRAM is at ~0.1 %% of peak" % float(batch.seqs.nbytes),
                      "kernel": "score_kernel<K,TRUNC,fwd> (forward score pass, all strip heights)",
                      "peak_source": "ssw_cuda_dpx_peak: %.3e VIADDMNMX.S16x2 lane-instr/s measured in this run / 3 per cell" % peak_lane,
                      "whole_step_frac": cells / (ms_step * 1e-3) / 1e9 / peak_gcups if world == 1 else None,

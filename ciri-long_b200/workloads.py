@@ -255,3 +255,33 @@ def bsj_refinement_pairs_torch(n_pairs, device, seed=SEED_BASE + 2, ref_len=2000
         p0 += k
     seqs = np.concatenate(blocks)
     return PairBatch(seqs, q_off, q_len, r_off, r_len, *params, name="C2-bsj-refinement")
+
+
+def concat_batches(batches, name="mixed", shuffle_seed=None):
+    """One batch out of several with the same scoring parameters (config C5 style mixtures)."""
+    p = (batches[0].match, batches[0].mismatch, batches[0].gap_open, batches[0].gap_extend)
+    for b in batches:
+        assert (b.match, b.mismatch, b.gap_open, b.gap_extend) == p, "a batch has one scoring scheme"
+    base = np.concatenate([[0], np.cumsum([len(b.seqs) for b in batches])])
+    seqs = np.concatenate([b.seqs for b in batches])
+    q_off = np.concatenate([b.q_off + base[i] for i, b in enumerate(batches)])
+    r_off = np.concatenate([b.r_off + base[i] for i, b in enumerate(batches)])
+    q_len = np.concatenate([b.q_len for b in batches])
+    r_len = np.concatenate([b.r_len for b in batches])
+    if shuffle_seed is not None:
+        perm = np.random.default_rng(shuffle_seed).permutation(len(q_len))
+        q_off, r_off, q_len, r_len = q_off[perm], r_off[perm], q_len[perm], r_len[perm]
+    return PairBatch(seqs, q_off, q_len, r_off, r_len, *p, name=name)
+
+
+def long_query_short_ref_pairs(n_pairs, seed=SEED_BASE + 7, q_min=200, q_max=5000, ref_len=50, params=(10, 4, 8, 2)):
+    """S4/S6-like pairs (collapse.py:251-256, 373-387): a 0.2-5 kb read against a 50-nt junction sequence."""
+    rng = np.random.default_rng(seed)
+    ql = rng.integers(q_min, q_max + 1, size=n_pairs)
+    q = rng.integers(0, 4, size=int(ql.sum()), dtype=np.int8)
+    q_off = np.cumsum(ql) - ql
+    st = (rng.random(n_pairs) * (ql - ref_len + 1)).astype(np.int64)
+    src = _ragged_arange(q_off + st, np.full(n_pairs, ref_len))
+    r_codes, r_len = noisy_channel(q[src], np.full(n_pairs, ref_len, dtype=np.int64), rng)
+    seqs, q_off2, r_off = _pack(q, ql.astype(np.int32), r_codes, r_len)
+    return PairBatch(seqs, q_off2, ql.astype(np.int32), r_off, r_len, *params, name="S4S6-long-query")

@@ -242,3 +242,14 @@ def test_batched_call_sites(sw, oracle):
     for span, rs, s in zip(spans, reads, sc):
         al = sw.Aligner(span * 2, 10, 4, 8, 2)
         assert abs(s - np.mean([al.align(r).score for r in rs])) < 1e-9
+
+
+def test_mixed_length_batch(sw, oracle):
+    """C5-style mixture under one scoring scheme: tiny junction pairs, read-vs-read segments, long reads vs
+    50-nt junctions, shuffled into one batch (every kernel instance and list class at once)"""
+    from ciri_long_b200 import workloads as W
+    b = W.concat_batches([W.junction_pairs(3000, seed=41), W.rolling_circle_pairs(40, seed=42, read_min=1500, read_max=5000),
+                          W.long_query_short_ref_pairs(300, seed=43), W.square_pairs(40, 700, seed=44, params=(10, 4, 8, 2))],
+                         shuffle_seed=45)
+    rng = np.random.default_rng(46)
+    check_batch(sw, oracle, b, sample=rng.choice(len(b), 500, replace=False))
