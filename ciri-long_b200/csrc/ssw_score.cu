@@ -169,16 +169,17 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
 
         // One wavefront step at offset t of the current chunk.
         //   CHECK = some lane may be outside [0, n) (pipeline fill and drain)
-        //   TOP   = strip 0 continues below the previous tile (reads the boundary array)
-        auto step = [&](auto chk, auto top, const int s, const int t) {
+        //   MULTI = the query spans several tiles: strip 0 may continue below the previous tile (boundary
+        //           array in), the last strip may feed the next tile (boundary array out)
+        auto step = [&](auto chk, auto multi, const int s, const int t) {
             constexpr bool CHECK = decltype(chk)::value;
-            constexpr bool TOP = decltype(top)::value;
+            constexpr bool MULTI = decltype(multi)::value;
             // hand-off from the previous strip (computed one step ago, same column as ours now)
             unsigned rH = __byte_perm(__shfl_sync(FULL, Hout, src), GO, fix);
             unsigned rF = __byte_perm(__shfl_sync(FULL, Fout, src), GO, fix);
             unsigned rR = __byte_perm(__shfl_sync(FULL, R, src), 0u, fix);
-            if (TOP) {
-                if (lane == 0 && s < n) {
+            if (MULTI) {
+                if (p > 0 && lane == 0 && s < n) {
                     const uint2 bv = bnd[s];
                     rH = (rH & 0xffff0000u) | (bv.x & 0xffffu);
                     rF = (rF & 0xffff0000u) | (bv.x >> 16);
@@ -266,7 +267,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             const unsigned wval = __byte_perm(R, Hout, selW);               // colmax | H(last row) << 16 of the writer's half
             bool colOk = isWriter;
             if (CHECK) colOk = colOk && (unsigned)(wHalf ? cHi : cLo) < (unsigned)n;
-            if (!lastTile) {
+            if (MULTI && !lastTile) {
                 if (colOk) wbnd[s] = make_uint2(__byte_perm(Hout, Fout, 0x7632u), R >> 16);   // always strip 63: high halves
             } else if (!REV) {
                 if (colOk) wcol[s] = wval;
@@ -286,7 +287,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             const int g = __reduce_max_sync(FULL, lo > hi ? lo : hi);
             bestT = max_relu(bestT, pack2(g, g));
         };
-        auto sweep = [&](auto top) {
+        auto sweep = [&](auto multi) {
             int s0 = 0;
             bool stop = false;
             while (s0 < steps && !stop) {
@@ -308,20 +309,20 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 if (steady) {
 #pragma unroll 2
                     for (int t = 0; t < len; ++t) {
-                        step(std::false_type{}, top, s0 + t, t);
+                        step(std::false_type{}, multi, s0 + t, t);
                         if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
                         if ((t & 31) == 31) refresh();
                     }
                 } else {
                     for (int t = 0; t < len; ++t) {
-                        step(std::true_type{}, top, s0 + t, t);
+                        step(std::true_type{}, multi, s0 + t, t);
                         if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
                     }
                 }
                 s0 = s1;
             }
         };
-        if (p > 0) sweep(std::true_type{}); else sweep(std::false_type{});
+        if (T > 1) sweep(std::true_type{}); else sweep(std::false_type{});
 
         // ---- tile epilogue: best cell of this tile in reference order (max, first column, first row)
         const int vlo = lo16(best) - go, vhi = hi16(best) - go;
