@@ -82,7 +82,7 @@ struct ssw_batch {
     int32_t *d_qlen = nullptr, *d_rlen = nullptr, *d_mask = nullptr;
     PairRec* d_rec = nullptr;
     // lists: [count | base | fill | cursor | count2 | cursor2] x N_LISTS
-    int32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_idx3 = nullptr, *d_meta = nullptr;
+    int32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_idx3 = nullptr, *d_idx4 = nullptr, *d_meta = nullptr;
     // scratch
     unsigned char* d_sscr[2] = {nullptr, nullptr};
     long long sstride[2] = {0, 0}, off_col[2] = {0, 0}, off_bnd[2] = {0, 0}, off_snap[2] = {0, 0};
@@ -99,6 +99,7 @@ struct ssw_batch {
     // host-side shape summary
     int max_q = 0, max_r = 0, maxK = 0;
     bool have[2][2][KMAX + 1];           // forward lists known to be non-empty: [cls][kind][K]
+    bool have_t2[2][KMAX + 1];           // GOTOH-first pairs that may overflow and move on to TRUNC: [cls][K]
     int64_t launches = 0;
     std::vector<PairRec> h_rec;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last run
@@ -107,6 +108,8 @@ struct ssw_batch {
     ListSet lists() const { return ListSet{d_idx, d_meta, d_meta + N_LISTS, d_meta + 2 * N_LISTS, d_meta + 3 * N_LISTS}; }
     int32_t* count2() const { return d_meta + 4 * N_LISTS; }
     int32_t* cursor2() const { return d_meta + 5 * N_LISTS; }
+    int32_t* count3() const { return d_meta + 6 * N_LISTS; }
+    int32_t* cursor3() const { return d_meta + 7 * N_LISTS; }
 };
 
 
@@ -134,7 +137,7 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaStream_t fs = b->stream;
     dev_free(b->d_seqs, fs); dev_free(b->d_qoff, fs); dev_free(b->d_roff, fs); dev_free(b->d_qlen, fs); dev_free(b->d_rlen, fs);
-    dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_meta, fs);
+    dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_idx4, fs); dev_free(b->d_meta, fs);
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
@@ -149,6 +152,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     TraceTimer tt("batch_alloc (validate+alloc+h2d enqueue)");
     b->h_mask.resize(n);
     memset(b->have, 0, sizeof b->have);
+    memset(b->have_t2, 0, sizeof b->have_t2);
     int maxScore = 0;
     for (int k = 0; k < 25; ++k) maxScore = std::max<int>(maxScore, b->sc.mat[k]);
     long long cig_worst = 16, q_total = 0;
@@ -165,9 +169,11 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         lo = std::min<long long>(lo, std::min(q_off[p], r_off[p]));
         hi = std::max<long long>(hi, std::max(q_off[p] + m, r_off[p] + r));
         if (m > 0 && r > 0) {
-            const int kind = (b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255) ? 1 : 0;
+            const int kind = first_pass_kind(m, b->sc.go, b->sc.ge, maxScore, b->sc.bias);
             const int K = strip_height_for(m, kind);
             b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
+            if (kind == 0 && b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255)
+                b->have_t2[r > LONG_REF_THRESHOLD ? 1 : 0][strip_height_for(m, 1)] = true;
             b->maxK = std::max(b->maxK, std::max(K, strip_height_for(m, 0)));
             cig_worst += 2LL * m + 3;
             q_total += m;
@@ -188,7 +194,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     CU_TRY(dev_alloc_t(&b->d_qlen, nn, st)); CU_TRY(dev_alloc_t(&b->d_rlen, nn, st)); CU_TRY(dev_alloc_t(&b->d_mask, nn, st));
     CU_TRY(dev_alloc_t(&b->d_rec, nn, st));
     CU_TRY(dev_alloc_t(&b->d_idx, nn, st)); CU_TRY(dev_alloc_t(&b->d_idx2, nn, st)); CU_TRY(dev_alloc_t(&b->d_idx3, 2 * nn, st));
-    CU_TRY(dev_alloc_t(&b->d_meta, 6 * N_LISTS, st));
+    CU_TRY(dev_alloc_t(&b->d_meta, 8 * N_LISTS, st)); CU_TRY(dev_alloc_t(&b->d_idx4, nn, st));
     CU_TRY(dev_alloc_t(&b->d_cigar_used, 1, st));
     CU_TRY(dev_alloc_t(&b->d_seqs, cap_seq, st));
     CU_TRY(cudaMemcpyAsync(b->d_qoff, q_off, (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -314,7 +320,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
     int launches = 0;
     const BatchView view = b->view();
     const ListSet ls = b->lists();
-    CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
+    CU_TRY(cudaMemsetAsync(b->count2(), 0, 4 * N_LISTS * 4, st));
     const size_t nn3 = ((size_t)std::max(b->n, 1) + 16383) & ~(size_t)16383;       // stride of the two hand-over lists in d_idx3
 
     auto score_args = [&](int cls) {
@@ -338,11 +344,25 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                 ScoreArgs a = score_args(cls);
                 a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
                 if (kind == 1) { a.next_idx = b->d_idx2; a.next_base = ls.base + id; a.next_count = b->count2() + id; }
+                else { a.next_idx = b->d_idx4; a.next_base = ls.base + id; a.next_count = b->count3() + id; }   // GOTOH overflow -> TRUNC
                 a.wide_idx = b->d_idx3 + (size_t)kind * nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + kind;
                 CU_TRY(launch_score(K, kind == 1, false, a, b->sblocks[cls], st));
                 ++launches;
             }
     CU_TRY(cudaEventRecord(b->ev[1], st));
+    // ---- pairs whose GOTOH-first pass overflowed 8 bits: the truncated-F pass gives their (word) result.
+    // strip heights of the two flavours agree for queries of up to 1024 rows, the only ones guessed GOTOH-first
+    for (int cls = 0; cls < 2; ++cls)
+        for (int K = 1; K <= KMAX; ++K) {
+            if (!b->have_t2[cls][K]) continue;
+            const int id = list_id(cls, 0, K);
+            ScoreArgs a = score_args(cls);
+            a.wl = WorkList{b->d_idx4, ls.base + id, b->count3() + id, b->cursor3() + id};
+            a.rerun = 1;
+            a.wide_idx = b->d_idx3 + nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + 1;
+            CU_TRY(launch_score(K, true, false, a, b->sblocks[cls], st));
+            ++launches;
+        }
     // ---- deciding byte-flavour pass for pairs whose truncated-F pass stayed below the 8-bit limit
     for (int cls = 0; cls < 2; ++cls)
         for (int K = 1; K <= KMAX; ++K) {

@@ -35,6 +35,15 @@ cudaError_t launch_score(int K, bool trunc, bool rev, const ScoreArgs& a, int bl
 
 cudaError_t launch_score32(bool trunc, bool rev, const ScoreArgs& a, int blocks, cudaStream_t st);
 
+// Which recurrence runs first on a pair when gap_open == gap_extend (0 = GOTOH, 1 = TRUNC).  Either order is
+// exact: a GOTOH pass that overflows 8 bits hands the pair to TRUNC, a TRUNC pass that stays below hands it
+// to the deciding GOTOH pass.  The guess only avoids the second pass: queries whose perfect-match score is
+// at least 4/3 of the 8-bit limit are expected to overflow (noisy long-read alignments score ~0.7 per base).
+__host__ __device__ inline int first_pass_kind(int m, int go, int ge, int maxScore, int bias)
+{
+    return (go == ge && 3LL * m * maxScore >= 4LL * (255 - bias)) ? 1 : 0;
+}
+
 // strip height (template parameter K of the score kernel) for a query of m rows; must match ssw_score.cu
 __host__ __device__ inline int strip_height_for(int m, int trunc)
 {

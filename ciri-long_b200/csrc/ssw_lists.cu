@@ -18,9 +18,8 @@ __device__ int classify(int stage, const BatchView& b, const Scoring& sc, int lo
     if (stage == 0) {
         const int m = b.q_len[p], n = b.r_len[p];
         if (m <= 0 || n <= 0) return -1;
-        // the word flavour with gap_open == gap_extend has its own recurrence; it can only be reached when the
-        // byte flavour can overflow at all: m * max(mat) + bias >= 255
-        const int kind = (sc.go == sc.ge && (long long)m * maxScore + sc.bias >= 255) ? 1 : 0;
+        // the word flavour with gap_open == gap_extend has its own recurrence (TRUNC); which one goes first is a guess
+        const int kind = first_pass_kind(m, sc.go, sc.ge, maxScore, sc.bias);
         return list_id(n > long_thr ? 1 : 0, kind, strip_height(m, kind));
     }
     // stage 1: reverse pass (ssw.c:834)

@@ -368,9 +368,14 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             // authoritative unless it overflows, in which case the word result already stored stands.
             if (over8) { if (lane == 0) rec->status &= ~PS_NEED_GOTOH; return; }
         } else if (!TRUNC && over8 && go == ge) {
-            status |= PS_PUNT;          // host routing guarantees this cannot happen; never guess
+            // the byte flavour overflows and the word flavour is the truncated-F recurrence: hand the pair over
+            if (lane == 0) {
+                const int pos = atomicAdd(a.next_count, 1);
+                a.next_idx[*a.next_base + pos] = pair;
+            }
+            return;
         }
-        if (TRUNC && !over8) status |= PS_NEED_GOTOH;
+        if (TRUNC && !over8 && !a.rerun) status |= PS_NEED_GOTOH;   // rerun = the byte pass already overflowed
         // near the range where the reference's 16-bit saturation (or this kernel's gate constant) matters:
         // the pair is re-done by the 32-bit kernel (ssw_score32.cu)
         const bool wide = candM >= (TRUNC ? TRUNC_SCORE_LIMIT : S16_SCORE_LIMIT) - go;
