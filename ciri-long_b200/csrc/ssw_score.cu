@@ -307,7 +307,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 rpCur = lds_u8(rpS);                                        // code of step s0 for my column
                 const int len = s1 - s0;
                 if (steady) {
-#pragma unroll 2
+#pragma unroll 8
                     for (int t = 0; t < len; ++t) {
                         step(std::false_type{}, multi, s0 + t, t);
                         if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
