@@ -401,7 +401,7 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(BAND_WARPS * 32) band_kernel(const BandArgs a)
+__global__ void __launch_bounds__(BAND_WARPS * 32, WIDE ? 1 : 4) band_kernel(const BandArgs a)
 {
     __shared__ uint4 window[BAND_WARPS][TB_WINDOW / 16];
     __shared__ uint2 stab[8];
