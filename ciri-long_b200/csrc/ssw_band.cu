@@ -48,12 +48,12 @@ struct BandJob {
 // (A C G T in .x, N in .y); a cell picks its score with one PRMT whose selector (base * 0x1111 + 0x8880:
 // byte index + sign replication) travels with the diagonal instead of the base code.
 // QUIRK = the band can be clipped by the reference end within the first w+1 rows (ssw.c:595-596 applies).
-template <int P, bool QUIRK>
+template <int DPL, bool QUIRK>
 __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, const int8_t* __restrict__ read,
                                               const int refLen, const int readLen, const int bw, const int go, const int ge,
                                               const uint2* stab, unsigned char* dir, const int rowStride, int maxv)
 {
-    constexpr int DPL = 2 * P;
+    constexpr int BPL = DPL == 3 ? 4 : DPL;                    // direction bytes per lane and row (3 is padded)
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
     const int kkBase = lane * DPL;
@@ -75,7 +75,7 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
     int i = -lane;                                              // my row in this iteration
     int jFirst = -lane + kkBase - bw;                           // column of my first diagonal in row i
     const int8_t* nextRef = ref + jFirst + DPL;                 // base entering my last diagonal in the next row
-    unsigned char* drow = dir + (long long)i * rowStride + kkBase;
+    unsigned char* drow = dir + (long long)i * rowStride + lane * BPL;
     // lane-constant part of cell validity: diagonal inside the band (0/1, applied by multiplication so
     // that it runs on the FMA pipe in the interior iterations)
     int vd[DPL];
@@ -147,7 +147,7 @@ __device__ __forceinline__ int band_fill_wave(const int8_t* __restrict__ ref, co
         lastH = Hl; lastF = Fl;
         if (INTERIOR ? vd[0] != 0 : rowOk) {
             if (DPL == 2) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)dirw[0];
-            else if (DPL == 4) *reinterpret_cast<unsigned*>(drow) = dirw[0];
+            else if (DPL == 3 || DPL == 4) *reinterpret_cast<unsigned*>(drow) = dirw[0];
             else if (DPL == 8) *reinterpret_cast<uint2*>(drow) = make_uint2(dirw[0], dirw[1]);
             else {
 #pragma unroll
@@ -283,23 +283,26 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
         jb.go = a.sc.go; jb.ge = a.sc.ge; jb.mat = a.sc.mat;
         const int readLen = jb.readLen, refLen = jb.refLen;
         int bw = refLen - readLen; if (bw < 0) bw = -bw; bw += 1;
-        int maxv = 0, rowStride = 0;
+        int maxv = 0, rowStride = 0, dpl = 0;
         if (WIDE) { bw = -rec->cigar_len; maxv = (int)rec->cigar_off; }
         unsigned char* dir = nullptr;
         for (;;) {
             const int Wd = 2 * bw + 1;
             jb.bw = bw;
-            int P = 0;                                           // diagonals per lane / 2; 0 = scan variant
-            if (Wd <= 64) P = 1; else if (Wd <= 128) P = 2; else if (Wd <= 256) P = 4;
-            else if (Wd <= 512) P = 8; else if (Wd <= 1024) P = 16;
-            if (!WIDE && (P == 0 || P > 2)) {
+            // diagonals per lane (0 = scan variant); at least 2, so that a lane's first cell has its vertical
+            // neighbour in the lane's own registers and the shuffle can sit between its first and last cell
+            int P = 0;
+            if (Wd <= 64) P = 2; else if (Wd <= 96) P = 3; else if (Wd <= 128) P = 4;
+            else if (Wd <= 256) P = 8; else if (Wd <= 512) P = 16; else if (Wd <= 1024) P = 32;
+            if (!WIDE && (P == 0 || P > 4)) {
                 if (lane == 0) {
                     rec->cigar_len = -bw; rec->cigar_off = maxv;
                     a.next_idx[atomicAdd(a.next_count, 1)] = pair;
                 }
                 return;
             }
-            rowStride = P ? 64 * P : ((Wd + 15) & ~15);
+            dpl = P;
+            rowStride = P ? 32 * (P == 3 ? 4 : P) : ((Wd + 15) & ~15);
             const long long rowBufBytes = P ? 0 : (((long long)(2 * bw + 4) * 8 + 15) & ~15LL);
             const long long need = rowBufBytes + (long long)rowStride * readLen;
             if (need > a.dir_bytes) { status = PS_BAND_SCRATCH; break; }
@@ -309,15 +312,19 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
 #define SSW_WAVE(PP) (q ? band_fill_wave<PP, true>(jb.ref, jb.read, refLen, readLen, bw, jb.go, jb.ge, stab, dir, rowStride, maxv) \
                         : band_fill_wave<PP, false>(jb.ref, jb.read, refLen, readLen, bw, jb.go, jb.ge, stab, dir, rowStride, maxv))
             if (!WIDE) {
-                if (P == 1) maxv = SSW_WAVE(1);
-                else maxv = SSW_WAVE(2);
+                switch (P) {
+                    case 2: maxv = SSW_WAVE(2); break;
+                    case 3: maxv = SSW_WAVE(3); break;
+                    default: maxv = SSW_WAVE(4); break;
+                }
             } else {
                 switch (P) {
-                    case 1: maxv = SSW_WAVE(1); break;
                     case 2: maxv = SSW_WAVE(2); break;
+                    case 3: maxv = SSW_WAVE(3); break;
                     case 4: maxv = SSW_WAVE(4); break;
                     case 8: maxv = SSW_WAVE(8); break;
                     case 16: maxv = SSW_WAVE(16); break;
+                    case 32: maxv = SSW_WAVE(32); break;
                     default: maxv = band_fill_scan(jb, reinterpret_cast<int*>(area), dir, rowStride, maxv); break;
                 }
             }
@@ -349,7 +356,8 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
                         const int beg = i - bw > 0 ? i - bw : 0;
                         const int end = i + bw < refLen - 1 ? i + bw : refLen - 1;
                         if (j < beg || j > end) { status = PS_TRACEBACK_ERR; break; }
-                        const int kk = j - i + bw;
+                        int kk = j - i + bw;
+                        if (dpl == 3) kk += kk / 3;                            // three diagonals per lane sit in four bytes
                         const int d = windowed ? win[(i - lo - 1) * rowStride + kk] : dir[(size_t)i * rowStride + kk];
                         int code;
                         if (state == 2) { const int dh = d >> 2; code = dh == 0 ? 1 : (dh == 1 ? 2 + (d & 1) : 4 + ((d >> 1) & 1)); }
