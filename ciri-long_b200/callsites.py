@@ -103,3 +103,102 @@ def curate_junction_batch(candidates, junc, distance, device=0):
         x = junc[alignment.query_begin:alignment.query_end]           # avg_score, collapse.py:156-158
         scores.append((i, j, distance(tmp, x) / len(tmp)))
     return sorted(scores, key=itemgetter(2))
+
+
+# ---- helpers the call sites below post-process with (restated; the reference keeps them in utils.py / align.py)
+def transform_seq(seq, bsj):
+    """CIRI_long/utils.py:123-124"""
+    return seq[bsj:] + seq[:bsj]
+
+
+def get_junc_seq(seq, bsj, width=25):
+    """CIRI_long/utils.py:127-140"""
+    st, en = bsj - width, bsj + width
+    if len(seq) <= 2 * width:
+        return seq[bsj - len(seq) // 2:] + seq[:bsj - len(seq) // 2]
+    if st < 0:
+        if en < 0:
+            return seq[st:en]
+        return seq[st:] + seq[:en]
+    if en > len(seq):
+        return seq[st:] + seq[:en - len(seq)]
+    return seq[st:en]
+
+
+_CIGAR_OPS = {c: k for k, c in enumerate("MIDNSHP=X")}
+
+
+def find_alignment_pos(alignment, pos):
+    """CIRI_long/align.py:803-820: query position aligned to reference position ``pos`` (None if outside)."""
+    import re
+    r_st = r_en = alignment.ref_begin
+    q_st = q_en = alignment.query_begin
+    for l, op in re.findall(r'(\d+)([MIDNSHP=X])', alignment.cigar_string):
+        l, op = int(l), _CIGAR_OPS[op]
+        if op == 0:
+            r_en += l; q_en += l
+        elif op == 1:
+            q_en += l
+        elif op == 2:
+            r_en += l
+        if r_st <= pos <= r_en:
+            return q_st + pos - r_st
+        r_st, q_st = r_en, q_en
+    return None
+
+
+def cluster_junction_seqs_batch(clusters, device=0):
+    """Batched head of ``collapse.correct_cluster`` (collapse.py:251-265) for several clusters at once.
+
+    clusters: list of ``(ref_seq, [query_seq, ...])`` -- the sequence of the longest 'full' read of the most
+    common circ_id, and the sequences of ``cluster[1:]`` (at least one, as the reference's ``max(head_pos)``
+    requires).  Two device batches instead of two per-read loops per cluster: every read against the first
+    50 nt of its cluster's reference (head position), then every read against the rotated template.
+    Returns one ``(template, junc_seqs)`` per cluster, ``junc_seqs`` being the list handed to ``spoa.poa``."""
+    refs, queries, owner = [], [], []
+    for c, (ref_seq, qs) in enumerate(clusters):
+        if not qs:
+            raise ValueError("cluster %d has no query reads (the reference fails on max([]) here)" % c)
+        for q in qs:
+            refs.append(ref_seq[:50]); queries.append(q); owner.append(c)
+    res = ssw_wrap.align_pairs(refs, queries, 10, 4, 8, 2, device=device, need_cigar=False)
+    head = [[] for _ in clusters]
+    for c, r in zip(owner, res):
+        head[c].append(r.ref_begin)
+    templates = [transform_seq(ref_seq, max(h)) for (ref_seq, _), h in zip(clusters, head)]
+    res = ssw_wrap.align_pairs([templates[c] for c in owner], queries, 10, 4, 8, 2, device=device, need_cigar=False)
+    out = [(t, [get_junc_seq(t, -max(h) // 2, 25)]) for t, h in zip(templates, head)]
+    for c, q, r in zip(owner, queries, res):
+        out[c][1].append(get_junc_seq(transform_seq(q, r.query_begin), -max(head[c]) // 2, 25))
+    return out
+
+
+def refined_sequences_batch(items, device=0):
+    """Batched rotation of the 'full' reads onto the curated junction (collapse.py:369-385).
+
+    items: list of ``(circ_junc_seq, [(read_id, seq), ...])`` -- ``genome_junction_seq(ctg, circ_start,
+    circ_end)`` and the (already sampled and sorted) full reads of the cluster.  This is the one CIRI-long
+    call site that reads the CIGAR.  Returns ``cluster_seq`` per item: ``[(read_id, rotated_seq), ...]``."""
+    refs, queries, owner = [], [], []
+    for c, (junc, reads) in enumerate(items):
+        for k, (_, seq) in enumerate(reads):
+            refs.append(junc); queries.append(seq * 2); owner.append((c, k))
+    res = ssw_wrap.align_pairs(refs, queries, 10, 4, 8, 2, report_cigar=True, device=device) if refs else []
+    out = [[None] * len(reads) for _, reads in items]
+    for (c, k), alignment in zip(owner, res):
+        junc, reads = items[c]
+        read_id, seq = reads[k]
+        tmp_pos = find_alignment_pos(alignment, len(junc) // 2)
+        out[c][k] = (read_id, seq) if tmp_pos is None else (read_id, transform_seq(seq, tmp_pos % len(seq)))
+    return out
+
+
+def exon_scores_batch(consensus_seq, exon_pair_seqs, device=0):
+    """Batched ``collapse.exon_score`` (collapse.py:760-774) for the candidates of one ``iter_flow`` step
+    (collapse.py:730,750,755): every candidate's concatenated (and, on the minus strand, reverse-complemented)
+    exon-pair sequence against the isoform consensus.  Returns ``ref_end - ref_begin`` per candidate."""
+    if not exon_pair_seqs:
+        return []
+    res = ssw_wrap.align_pairs([consensus_seq] * len(exon_pair_seqs), exon_pair_seqs, 10, 4, 8, 2, device=device,
+                               need_cigar=False, _shared_ref=True)
+    return [r.ref_end - r.ref_begin for r in res]

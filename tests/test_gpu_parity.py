@@ -244,6 +244,81 @@ def test_batched_call_sites(sw, oracle):
         assert abs(s - np.mean([al.align(r).score for r in rs])) < 1e-9
 
 
+class _OracleAlignment:
+    """what the reference's PyAlignRes exposes, filled from the CPU oracle (independent of the CUDA path)"""
+    def __init__(self, oracle, ref, query, p):
+        r = oracle.align(O.encode(query), O.encode(ref), O.make_mat(p[0], p[1]), p[2], p[3], flag=1)
+        self.score, self.ref_begin, self.ref_end = r["score"], r["ref_begin"], r["ref_end"]
+        self.query_begin, self.query_end = r["read_begin"], r["read_end"]
+        self.cigar_string = O.cigar_string(r, len(query))
+
+
+def test_batched_collapse_call_sites(sw, oracle):
+    """callsites.py: correct_cluster head / refined sequences / exon_score in two-phase form against the
+    reference's per-read loops (collapse.py:251-265, 369-385, 760-774) driven by the CPU oracle"""
+    from ciri_long_b200 import callsites as cs
+    from ciri_long_b200.workloads import noisy_channel
+    rng = np.random.default_rng(99)
+    bases = np.array(list("ACGT"))
+    P = (10, 4, 8, 2)
+
+    def noisy(seq):
+        codes, _ = noisy_channel(O.encode(seq), np.array([len(seq)]), rng)
+        return "".join("ACGTN"[c] for c in codes)
+
+    clusters = []
+    for c in range(6):
+        L = int(rng.integers(260, 900))
+        circ = "".join(bases[rng.integers(0, 4, L)])
+        reads = []
+        for _ in range(int(rng.integers(2, 7))):
+            rot = int(rng.integers(0, L))
+            reads.append(noisy(circ[rot:] + circ[:rot]))
+        clusters.append((reads[0], reads[1:]))
+    got = cs.cluster_junction_seqs_batch(clusters)
+    for (ref_seq, qs), (template, juncs) in zip(clusters, got):
+        head_pos = [_OracleAlignment(oracle, ref_seq[:50], q, P).ref_begin for q in qs]
+        exp_template = cs.transform_seq(ref_seq, max(head_pos))
+        exp = [cs.get_junc_seq(exp_template, -max(head_pos) // 2, 25)]
+        for q in qs:
+            al = _OracleAlignment(oracle, exp_template, q, P)
+            exp.append(cs.get_junc_seq(cs.transform_seq(q, al.query_begin), -max(head_pos) // 2, 25))
+        assert template == exp_template and juncs == exp
+
+    items = []
+    for c in range(5):
+        L = int(rng.integers(200, 700))
+        circ = "".join(bases[rng.integers(0, 4, L)])
+        junc = circ[-25:] + circ[:25]                                 # genome_junction_seq: 25 nt either side of the BSJ
+        reads = []
+        for k in range(int(rng.integers(1, 6))):
+            rot = int(rng.integers(0, L))
+            reads.append(("read%d_%d" % (c, k), noisy(circ[rot:] + circ[:rot])))
+        reads.append(("unrelated%d" % c, "".join(bases[rng.integers(0, 4, 120)])))
+        items.append((junc, reads))
+    got = cs.refined_sequences_batch(items)
+    n_rotated = 0
+    for (junc, reads), res in zip(items, got):
+        for (rid, seq), g in zip(reads, res):
+            al = _OracleAlignment(oracle, junc, seq * 2, P)
+            pos = cs.find_alignment_pos(al, len(junc) // 2)
+            exp = (rid, seq) if pos is None else (rid, cs.transform_seq(seq, pos % len(seq)))
+            n_rotated += pos is not None
+            assert g == exp
+    assert n_rotated > 5
+
+    cons = "".join(bases[rng.integers(0, 4, 900)])
+    exon_pairs = [noisy(cons[a:a + 120] + cons[b:b + 150]) for a, b in ((0, 300), (100, 500), (350, 700), (20, 200))]
+    exon_pairs.append(cs.revcomp(cons[50:400]))
+    got = cs.exon_scores_batch(cons, exon_pairs)
+    exp = []
+    for q in exon_pairs:
+        al = _OracleAlignment(oracle, cons, q, P)
+        exp.append(al.ref_end - al.ref_begin)
+    assert got == exp
+    assert cs.exon_scores_batch(cons, []) == []
+
+
 def test_mixed_length_batch(sw, oracle):
     """C5-style mixture under one scoring scheme: tiny junction pairs, read-vs-read segments, long reads vs
     50-nt junctions, shuffled into one batch (every kernel instance and list class at once)"""
