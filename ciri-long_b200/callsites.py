@@ -88,20 +88,24 @@ def junc_score_batch(genomic_spans, junc_seq_lists, device=0):
     return (sums / np.maximum(cnt, 1)).tolist()
 
 
-def curate_junction_batch(candidates, junc, distance, device=0):
+def curate_junction_batch(candidates, junc, distance=None, device=0):
     """Batched ``collapse.curate_junction`` (collapse.py:161-173).
 
     candidates: list of (i, j, genomic_junction_seq) — the 20-nt ``genome_junction_seq(ctg, i, j, width=10)``
-    of every (i, j) the reference's double loop visits; junc: the POA junction consensus; distance: the
-    edit-distance function of ``utils.distance`` (edlib / Levenshtein, not vendored by the reference).
+    of every (i, j) the reference's double loop visits; junc: the POA junction consensus; distance: a
+    per-pair edit-distance function with the meaning of ``utils.distance``; by default the distances of all
+    candidates are computed in one device batch (``distance.distance_batch``).
     Returns ``sorted([(i, j, avg_score)], key=score)`` like the reference."""
     from operator import itemgetter
     refs = [c[2] for c in candidates]
     res = ssw_wrap.align_pairs(refs, [junc] * len(refs), 10, 4, 8, 2, device=device, need_cigar=False) if refs else []
-    scores = []
-    for (i, j, tmp), alignment in zip(candidates, res):
-        x = junc[alignment.query_begin:alignment.query_end]           # avg_score, collapse.py:156-158
-        scores.append((i, j, distance(tmp, x) / len(tmp)))
+    pieces = [junc[alignment.query_begin:alignment.query_end] for alignment in res]     # avg_score, collapse.py:156-158
+    if distance is None:
+        from .distance import distance_batch
+        dists = distance_batch(refs, pieces, device) if refs else []
+    else:
+        dists = [distance(tmp, x) for tmp, x in zip(refs, pieces)]
+    scores = [(i, j, int(d) / len(tmp)) for (i, j, tmp), d in zip(candidates, dists)]
     return sorted(scores, key=itemgetter(2))
 
 

@@ -603,6 +603,110 @@ extern "C" void ssw_encode_dna(const char* ascii, int64_t len, int8_t* codes)
     for (int64_t k = 0; k < len; ++k) codes[k] = lut[(unsigned char)ascii[k]];
 }
 
+// ---- batched edit distance (CIRI_long/utils.py:153-159) -------------------
+// One call: upload the referenced bytes, classify the pairs by the length of their shorter string into
+// the kernel instances of edit_distance.cu, run them on one stream, copy the distances back.
+extern "C" int ssw_cuda_edit_distance_batch(int device, int32_t n_pairs, const uint8_t* seqs, int64_t seqs_len,
+                                            const int64_t* x_off, const int32_t* x_len,
+                                            const int64_t* y_off, const int32_t* y_len, int32_t* out)
+{
+    if (n_pairs < 0 || (n_pairs > 0 && (!seqs || !x_off || !x_len || !y_off || !y_len || !out))) {
+        set_error("ssw_cuda_edit_distance_batch: null argument");
+        return SSW_ERR_ARG;
+    }
+    if (n_pairs == 0) return SSW_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("ssw_cuda_edit_distance_batch: no CUDA device (this library has no CPU path)");
+        return SSW_ERR_NODEVICE;
+    }
+    CU_TRY(cudaSetDevice(device));
+    // byte range referenced by the batch, symbols that occur in it, work lists per kernel instance
+    long long lo = seqs_len, hi = 0;
+    std::vector<int32_t> lists[6];
+    long long maxText5 = 0;
+    bool seen[256] = {false};
+    for (int32_t p = 0; p < n_pairs; ++p) {
+        const long long xl = x_len[p], yl = y_len[p];
+        if (xl < 0 || yl < 0 || x_off[p] < 0 || y_off[p] < 0 || x_off[p] + xl > seqs_len || y_off[p] + yl > seqs_len) {
+            set_error("ssw_cuda_edit_distance_batch: pair " + std::to_string(p) + " lies outside the sequence buffer");
+            return SSW_ERR_ARG;
+        }
+        if (xl) { lo = std::min<long long>(lo, x_off[p]); hi = std::max<long long>(hi, x_off[p] + xl); }
+        if (yl) { lo = std::min<long long>(lo, y_off[p]); hi = std::max<long long>(hi, y_off[p] + yl); }
+        const long long mm = std::min(xl, yl);
+        const int kind = mm <= 32 ? 0 : mm <= 64 ? 1 : mm <= 128 ? 2 : mm <= 256 ? 3 : mm <= 512 ? 4 : 5;
+        lists[kind].push_back(p);
+        if (kind == 5) maxText5 = std::max(maxText5, std::max(xl, yl));
+    }
+    if (hi < lo) { lo = 0; hi = 0; }
+    for (long long k = lo; k < hi; ++k) seen[seqs[k]] = true;
+    EditArgs ea;
+    int nsym = 0;
+    for (int b = 0; b < 256; ++b) {
+        ea.code[b] = 0;
+        if (seen[b]) {
+            if (nsym == ED_MAXSYM) {
+                set_error("ssw_cuda_edit_distance_batch: more than 16 distinct symbols in the batch");
+                return SSW_ERR_UNSUPPORTED;
+            }
+            ea.code[b] = (unsigned char)nsym++;
+        }
+    }
+    cudaStream_t st = nullptr;
+    CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    unsigned char* d_seqs = nullptr;
+    int64_t *d_xoff = nullptr, *d_yoff = nullptr;
+    int32_t *d_xlen = nullptr, *d_ylen = nullptr, *d_out = nullptr, *d_idx = nullptr;
+    signed char* d_carry = nullptr;
+    int rc = SSW_OK;
+    auto body = [&]() -> int {
+        CU_TRY(dev_alloc_t(&d_seqs, (size_t)(hi - lo), st));
+        CU_TRY(dev_alloc_t(&d_xoff, n_pairs, st)); CU_TRY(dev_alloc_t(&d_yoff, n_pairs, st));
+        CU_TRY(dev_alloc_t(&d_xlen, n_pairs, st)); CU_TRY(dev_alloc_t(&d_ylen, n_pairs, st));
+        CU_TRY(dev_alloc_t(&d_out, n_pairs, st)); CU_TRY(dev_alloc_t(&d_idx, n_pairs, st));
+        if (hi > lo) CU_TRY(cudaMemcpyAsync(d_seqs, seqs + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_xoff, x_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_yoff, y_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_xlen, x_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_ylen, y_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+        ea.seqs = d_seqs - lo; ea.x_off = d_xoff; ea.x_len = d_xlen; ea.y_off = d_yoff; ea.y_len = d_ylen;
+        ea.out = d_out; ea.carry = nullptr; ea.carry_stride = 0;
+        long long at = 0;
+        for (int kind = 0; kind < 6; ++kind) {
+            const long long cnt = (long long)lists[kind].size();
+            if (!cnt) continue;
+            CU_TRY(cudaMemcpyAsync(d_idx + at, lists[kind].data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, st));
+            ea.idx = d_idx + at; ea.count = (int32_t)cnt;
+            long long blocks;
+            if (kind < 2) blocks = std::min<long long>((cnt + EDIT_THREADS - 1) / EDIT_THREADS, (long long)sms * 16);
+            else {
+                const int groupsPerBlock = (EDIT_THREADS / 32) * (32 / (4 << (kind - 2)));
+                blocks = std::min<long long>((cnt + groupsPerBlock - 1) / groupsPerBlock, (long long)sms * 8);
+            }
+            blocks = std::max<long long>(blocks, 1);
+            if (kind == 5) {
+                ea.carry_stride = (maxText5 + 255) & ~255LL;
+                CU_TRY(dev_alloc_t(&d_carry, (size_t)(blocks * (EDIT_THREADS / 32) * ea.carry_stride), st));
+                ea.carry = d_carry;
+            }
+            CU_TRY(launch_edit(kind, ea, (int)blocks, st));
+            at += cnt;
+        }
+        CU_TRY(cudaMemcpyAsync(out, d_out, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        return SSW_OK;
+    };
+    rc = body();
+    dev_free(d_seqs, st); dev_free(d_xoff, st); dev_free(d_yoff, st); dev_free(d_xlen, st); dev_free(d_ylen, st);
+    dev_free(d_out, st); dev_free(d_idx, st); dev_free(d_carry, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
 extern "C" int ssw_cuda_device_count(void)
 {
     int n = 0;

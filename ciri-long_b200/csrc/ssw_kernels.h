@@ -95,6 +95,25 @@ constexpr int BAND_WARPS = 8;
 // wide = false: bands up to 128 diagonals; wide = true: everything the narrow launch handed over
 cudaError_t launch_band(bool wide, const BandArgs& a, int blocks, cudaStream_t st);
 
+// ---- batched edit distance (edit_distance.cu)
+constexpr int ED_MAXSYM = 16;          // distinct symbols per batch (4-bit codes)
+constexpr int EDIT_THREADS = 128;
+struct EditArgs {
+    const unsigned char* seqs;     // raw bytes, indexed with the caller's offsets
+    const int64_t* x_off;
+    const int32_t* x_len;
+    const int64_t* y_off;
+    const int32_t* y_len;
+    int32_t* out;
+    const int32_t* idx;            // pairs of this launch
+    int32_t count;
+    signed char* carry;            // tiled instance: one horizontal delta per text column and warp
+    long long carry_stride;
+    unsigned char code[256];       // byte -> dense symbol code
+};
+// kind 0/1: one thread per pair, pattern <= 32 / <= 64; kind 2..5: 4/8/16/32 lanes per pair
+cudaError_t launch_edit(int kind, const EditArgs& a, int blocks, cudaStream_t st);
+
 // ---- DPX issue-rate probe (ssw_peak.cu)
 cudaError_t dpx_peak_probe(double* lane_instr_per_s, cudaStream_t st);
 

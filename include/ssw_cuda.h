@@ -147,6 +147,15 @@ void ssw_encode_dna(const char* ascii, int64_t len, int8_t* codes);
 
 /* Diagnostics */
 const char* ssw_cuda_last_error(void);
+/* Batched unit-cost global edit distance.  Replaces
+ * CIRI_long/utils.py:153-159 `distance(x, y)` -- Levenshtein.distance / edlib.align(...)['editDistance'],
+ * the same quantity -- as called per pair from collapse.py:156-158 and collapse.py:466-473.
+ * seqs: raw bytes (symbols are compared for equality; at most 16 distinct byte values per batch),
+ * pair p = seqs[x_off[p] .. +x_len[p]) vs seqs[y_off[p] .. +y_len[p]); out[p] = distance.
+ * Returns SSW_OK or an SSW_ERR_* code (ssw_cuda_last_error() says why). */
+int ssw_cuda_edit_distance_batch(int device, int32_t n_pairs, const uint8_t* seqs, int64_t seqs_len,
+                                 const int64_t* x_off, const int32_t* x_len,
+                                 const int64_t* y_off, const int32_t* y_len, int32_t* out);
 int ssw_cuda_device_count(void);
 /* Measured issue rate of a dependency-free VIADDMNMX.S16x2 stream on `device`, in 32-bit
  * lane-instructions per second (the denominator of the DPX roofline). */

@@ -215,3 +215,15 @@ def same(a, b, with_cigar=True):
         if a[k] != b[k]:
             return False
     return (not with_cigar) or list(a["cigar"]) == list(b["cigar"])
+
+
+def edit_distance(x, y):
+    """Unit-cost global edit distance of two byte strings (oracle/edit_oracle.c; CIRI_long/utils.py:153-159)."""
+    lib = C.CDLL(ORACLE_SO)
+    lib.orc_edit_distance.restype = C.c_int32
+    lib.orc_edit_distance.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+    if isinstance(x, str):
+        x = x.encode("latin-1")
+    if isinstance(y, str):
+        y = y.encode("latin-1")
+    return int(lib.orc_edit_distance(bytes(x), len(x), bytes(y), len(y)))

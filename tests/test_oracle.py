@@ -79,3 +79,36 @@ def test_batch_driver_matches_single(oracle):
         assert rec["score1"][i] == a["score"] and rec["ref_begin1"][i] == a["ref_begin"]
         assert rec["read_end1"][i] == a["read_end"] and rec["ref_end2"][i] == a["ref_end2"]
         assert cig[rec["cigar_off"][i]:rec["cigar_off"][i] + rec["cigar_len"][i]].tolist() == a["cigar"]
+
+
+def _py_edit_distance(x, y):
+    """independent restatement (full matrix, pure Python) used only to cross-check the C checker"""
+    D = [[0] * (len(y) + 1) for _ in range(len(x) + 1)]
+    for i in range(len(x) + 1):
+        D[i][0] = i
+    for j in range(len(y) + 1):
+        D[0][j] = j
+    for i in range(1, len(x) + 1):
+        for j in range(1, len(y) + 1):
+            D[i][j] = min(D[i - 1][j] + 1, D[i][j - 1] + 1, D[i - 1][j - 1] + (x[i - 1] != y[j - 1]))
+    return D[len(x)][len(y)]
+
+
+def test_edit_distance_oracle_known_answers_and_properties():
+    """oracle/edit_oracle.c (utils.py:153-159): published known answers, an independent restatement, metric
+    properties.  edlib / python-Levenshtein themselves are absent from this image."""
+    O.build(ref=False)
+    for x, y, d in (("kitten", "sitting", 3), ("flaw", "lawn", 2), ("intention", "execution", 5),
+                    ("GATTACA", "GCATGCU", 4), ("sunday", "saturday", 3), ("", "", 0), ("", "abc", 3), ("abc", "", 3),
+                    ("ACGT", "ACGT", 0), ("acgt", "ACGT", 4)):
+        assert O.edit_distance(x, y) == d
+    rng = np.random.default_rng(3)
+    seqs = ["".join(np.array(list("ACGTN"))[rng.integers(0, 5, int(rng.integers(0, 70)))]) for _ in range(40)]
+    for a in seqs[:20]:
+        for b in seqs[20:]:
+            d = O.edit_distance(a, b)
+            assert d == _py_edit_distance(a, b)
+            assert d == O.edit_distance(b, a)
+            assert abs(len(a) - len(b)) <= d <= max(len(a), len(b))
+    a, b, c = seqs[1], seqs[2], seqs[3]
+    assert O.edit_distance(a, c) <= O.edit_distance(a, b) + O.edit_distance(b, c)
