@@ -110,31 +110,40 @@ __global__ void __launch_bounds__(EDIT_THREADS) edit_group_kernel(const EditArgs
             // the word that holds the tile's last row hands its delta to the next tile (or to the score)
             const bool tail = mine && (base + 32 >= m || g == G - 1);
             const unsigned topBit = rows ? rows - 1 : 0;
+            const unsigned* myPeq = &peq[warp][0][lane];
             unsigned Pv = 0xffffffffu, Mv = 0;
-            int hout = 0, c = 0;
+            // horizontal deltas travel as two bits: bit 0 = +1, bit 1 = -1
+            unsigned hout = 0, c = 0, symv = 0, carv = 1;
             for (int s = 0; s < maxSteps; ++s) {
-                int cin = __shfl_up_sync(FULL, c, 1, G);
-                int hin = __shfl_up_sync(FULL, hout, 1, G);
-                if (g == 0) {
-                    cin = s < n ? code[txt[s]] : 0;
-                    hin = (t == 0 || s >= n) ? 1 : (int)carry[s];
+                if ((s & (G - 1)) == 0) {
+                    // every G steps the group fetches the next G text symbols (and, below the first tile,
+                    // the deltas the tile above left for these columns), one per lane
+                    const int col = s + g;
+                    symv = col < n ? code[txt[col]] : 0;
+                    carv = (t > 0 && col < n) ? (unsigned)carry[col] : 1u;
                 }
+                unsigned cin = __shfl_up_sync(FULL, c, 1, G);
+                unsigned hin = __shfl_up_sync(FULL, hout, 1, G);
+                const unsigned c0 = __shfl_sync(FULL, symv, s & (G - 1), G);
+                const unsigned h0 = __shfl_sync(FULL, carv, s & (G - 1), G);
+                if (g == 0) { cin = c0; hin = h0; }
                 c = cin;
                 const int j = s - g;
-                if (mine && j >= 0 && j < n) {
-                    unsigned Eq = peq[warp][c][lane];
+                if ((unsigned)j < (unsigned)n) {
+                    const unsigned hp = hin & 1u, hm = hin >> 1;
+                    unsigned Eq = myPeq[c * 32];
                     const unsigned Xv = Eq | Mv;
-                    if (hin < 0) Eq |= 1u;
+                    Eq |= hm;
                     const unsigned Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
                     unsigned Ph = Mv | ~(Xh | Pv);
                     unsigned Mh = Pv & Xh;
-                    hout = (int)((Ph >> topBit) & 1u) - (int)((Mh >> topBit) & 1u);
-                    Ph <<= 1; Mh <<= 1;
-                    if (hin < 0) Mh |= 1u; else if (hin > 0) Ph |= 1u;
+                    hout = ((Ph >> topBit) & 1u) | (((Mh >> topBit) & 1u) << 1);
+                    Ph = (Ph << 1) | hp;
+                    Mh = (Mh << 1) | hm;
                     Pv = Mh | ~(Xv | Ph);
                     Mv = Ph & Xv;
                     if (tail) {
-                        if (lastTile) score += hout;
+                        if (lastTile) score += (int)(hout & 1u) - (int)(hout >> 1);
                         else carry[j] = (signed char)hout;
                     }
                 }
