@@ -213,7 +213,15 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         if (!any) continue;
         const int ncap = cls == 0 ? std::min(cap_r, LONG_REF_THRESHOLD) : cap_r;
         b->sstride[cls] = score_scratch_layout(ncap, &b->off_col[cls], &b->off_bnd[cls], &b->off_snap[cls]);
-        long long blocks = SCRATCH_BUDGET / (b->sstride[cls] * SCORE_WARPS);
+        // long references need megabytes of column records per resident warp: let them take up to a quarter
+        // of the free HBM, so that every SM keeps its full set of warps
+        long long budget = SCRATCH_BUDGET;
+        if (cls == 1) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                budget = std::max<long long>(budget, std::min<long long>((long long)(free_b / 4), 40LL << 30));
+        }
+        long long blocks = budget / (b->sstride[cls] * SCORE_WARPS);
         blocks = std::max<long long>(1, std::min<long long>(blocks, b->sms));
         blocks = std::min<long long>(blocks, (n + 15) / 16);
         b->sblocks[cls] = (int)blocks;
