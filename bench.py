@@ -301,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "dpx", "achieved": fwd_gcups, "peak": peak_gcups, "unit": "GCUPS",
                      "frac": fwd_gcups / peak_gcups, "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step, from the "
-                                     "committed ncu capture profiles/r1_final_launches_1M.csv (bytes); algorithmic input is "
+                                     "committed ncu capture profiles/r1_v10_launches_1M.csv (bytes); algorithmic input is "
                                      "%.2e bytes per step: the pass is DPX-bound, DRAM is at ~0.1 %% of peak" % float(batch.seqs.nbytes),
                      "kernel": "score_kernel<K,TRUNC,fwd> (forward score pass, all strip heights)",
                      "peak_source": "ssw_cuda_dpx_peak: %.3e VIADDMNMX.S16x2 lane-instr/s measured in this run / 3 per cell" % peak_lane,
