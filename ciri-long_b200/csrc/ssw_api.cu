@@ -77,6 +77,7 @@ struct ssw_batch {
     // d_seqs - seq_lo so the caller's offsets are used unchanged)
     long long seq_lo = 0, seq_hi = 0;
     std::vector<int32_t> h_mask;
+    std::vector<int64_t> h_col_off;
     int8_t* d_seqs = nullptr;
     long long *d_qoff = nullptr, *d_roff = nullptr;
     int32_t *d_qlen = nullptr, *d_rlen = nullptr, *d_mask = nullptr;
@@ -100,6 +101,18 @@ struct ssw_batch {
     int max_q = 0, max_r = 0, maxK = 0;
     bool have[2][2][KMAX + 1];           // forward lists known to be non-empty: [cls][kind][K]
     bool have_t2[2][KMAX + 1];           // GOTOH-first pairs that may overflow and move on to TRUNC: [cls][K]
+    // long references (class 1): forward pass over column chunks (ssw_kernels.h: ChunkPlan)
+    int32_t chunk_cols = 0;
+    int32_t long_pairs[2][KMAX + 1];     // class-1 pairs per forward list [kind][K]
+    long long task_cap[2][KMAX + 1];     // and the tasks they expand to
+    long long task_base[2][KMAX + 1];    // region of each list inside the task tables
+    int64_t* d_col_off = nullptr;
+    unsigned* d_col_pool = nullptr;
+    unsigned long long* d_pair_key = nullptr;
+    int32_t* d_pair_left = nullptr;
+    int32_t* d_task = nullptr;           // task_pair | task_c0 | task_c1, each task_total entries
+    long long task_total = 0;
+    int32_t* d_task_meta = nullptr;      // counts[2][KMAX+1] | cursors[2][KMAX+1]
     int64_t launches = 0;
     std::vector<PairRec> h_rec;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last run
@@ -138,6 +151,8 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     cudaStream_t fs = b->stream;
     dev_free(b->d_seqs, fs); dev_free(b->d_qoff, fs); dev_free(b->d_roff, fs); dev_free(b->d_qlen, fs); dev_free(b->d_rlen, fs);
     dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_idx4, fs); dev_free(b->d_meta, fs);
+    dev_free(b->d_col_off, fs); dev_free(b->d_col_pool, fs); dev_free(b->d_pair_key, fs); dev_free(b->d_pair_left, fs);
+    dev_free(b->d_task, fs); dev_free(b->d_task_meta, fs);
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
@@ -157,6 +172,21 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     for (int k = 0; k < 25; ++k) maxScore = std::max<int>(maxScore, b->sc.mat[k]);
     long long cig_worst = 16, q_total = 0;
     long long lo = seqs_len, hi = 0;
+    long long long_cols = 0;
+    memset(b->long_pairs, 0, sizeof b->long_pairs);
+    for (int32_t p = 0; p < n; ++p) if (q_len[p] > 0 && r_len[p] > LONG_REF_THRESHOLD) long_cols += r_len[p];
+    if (long_cols > 0) {
+        // enough tasks to fill the machine a few times over, chunks long enough to amortise the overlap
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+        long long c = long_cols / (8LL * std::max(sms, 1) * SCORE_WARPS);
+        c = std::max<long long>(8192, std::min<long long>(c, 65536));
+        b->chunk_cols = (int32_t)((c + RP_CHUNK - 1) / RP_CHUNK * RP_CHUNK);
+    }
+    memset(b->task_cap, 0, sizeof b->task_cap);
+    std::vector<int64_t> h_col_off;
+    long long col_total = 0;
+    if (b->chunk_cols) h_col_off.assign(n, 0);
     for (int32_t p = 0; p < n; ++p) {
         const int m = q_len[p], r = r_len[p];
         if (m < 0 || r < 0 || q_off[p] < 0 || r_off[p] < 0 || q_off[p] + m > seqs_len || r_off[p] + r > seqs_len) {
@@ -172,6 +202,12 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
             const int kind = first_pass_kind(m, b->sc.go, b->sc.ge, maxScore, b->sc.bias);
             const int K = strip_height_for(m, kind);
             b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
+            if (r > LONG_REF_THRESHOLD) {
+                b->long_pairs[kind][K] += 1;
+                b->task_cap[kind][K] += chunk_tasks(m, r, b->chunk_cols, maxScore, b->sc.ge);
+                h_col_off[p] = col_total;
+                col_total += ((long long)r + 31) & ~31LL;             // 128-byte aligned: no cache line is shared by two pairs
+            }
             if (kind == 0 && b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255)
                 b->have_t2[r > LONG_REF_THRESHOLD ? 1 : 0][strip_height_for(m, 1)] = true;
             b->maxK = std::max(b->maxK, std::max(K, strip_height_for(m, 0)));
@@ -206,6 +242,20 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     // asynchronous (the caller keeps `seqs` alive until ssw_batch_fetch, like every CUDA async copy)
     if (hi > lo) CU_TRY(cudaMemcpyAsync(b->d_seqs, seqs + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
 
+    if (b->chunk_cols) {
+        b->task_total = 0;
+        for (int kind = 0; kind < 2; ++kind)
+            for (int K = 1; K <= KMAX; ++K) { b->task_base[kind][K] = b->task_total; b->task_total += b->task_cap[kind][K]; }
+        CU_TRY(dev_alloc_t(&b->d_col_off, nn, st));
+        CU_TRY(dev_alloc_t(&b->d_col_pool, (size_t)col_total + 64, st));
+        CU_TRY(dev_alloc_t(&b->d_pair_key, nn, st));
+        CU_TRY(dev_alloc_t(&b->d_pair_left, nn, st));
+        CU_TRY(dev_alloc_t(&b->d_task, (size_t)(3 * b->task_total + 16), st));
+        CU_TRY(dev_alloc_t(&b->d_task_meta, 4 * (KMAX + 1), st));
+        // (the vector dies with this function: the copy is made from a staging allocation that outlives it)
+        b->h_col_off.swap(h_col_off);
+        CU_TRY(cudaMemcpyAsync(b->d_col_off, b->h_col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    }
     // score-pass scratch: class 0 = references up to LONG_REF_THRESHOLD columns, class 1 = longer ones
     for (int cls = 0; cls < 2; ++cls) {
         bool any = false;
@@ -338,7 +388,28 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         a.off_col = b->off_col[cls]; a.off_bnd = b->off_bnd[cls]; a.off_snap = b->off_snap[cls];
         a.rerun = 0; a.next_idx = nullptr; a.next_base = nullptr; a.next_count = nullptr;
         a.wide_idx = nullptr; a.wide_count = nullptr;
+        memset(&a.ck, 0, sizeof a.ck);
         return a;
+    };
+
+    // class-1 forward launches: expand the pair list into column-chunk tasks and let the kernel walk those
+    int maxScore = 0;
+    for (int k = 0; k < 25; ++k) maxScore = std::max<int>(maxScore, b->sc.mat[k]);
+    auto chunk_launch = [&](ScoreArgs& a, int kind, int K) -> int {
+        if (!b->chunk_cols || !b->long_pairs[kind][K]) return SSW_OK;
+        int32_t* cnt = b->d_task_meta + kind * (KMAX + 1) + K;
+        int32_t* cur = b->d_task_meta + 2 * (KMAX + 1) + kind * (KMAX + 1) + K;
+        CU_TRY(cudaMemsetAsync(cnt, 0, 4, st));
+        CU_TRY(cudaMemsetAsync(cur, 0, 4, st));
+        a.ck.chunk_cols = b->chunk_cols; a.ck.max_match = maxScore;
+        a.ck.task_pair = b->d_task + b->task_base[kind][K];
+        a.ck.task_c0 = b->d_task + b->task_total + b->task_base[kind][K];
+        a.ck.task_c1 = b->d_task + 2 * b->task_total + b->task_base[kind][K];
+        a.ck.pair_key = b->d_pair_key; a.ck.pair_left = b->d_pair_left;
+        a.ck.col_off = b->d_col_off; a.ck.col_pool = b->d_col_pool;
+        CU_TRY(expand_tasks(a.wl, b->long_pairs[kind][K], view, b->sc, a.ck, cnt, st, &launches));
+        a.wl = WorkList{nullptr, nullptr, cnt, cur};
+        return SSW_OK;
     };
 
     // ---- forward pass
@@ -354,6 +425,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                 if (kind == 1) { a.next_idx = b->d_idx2; a.next_base = ls.base + id; a.next_count = b->count2() + id; }
                 else { a.next_idx = b->d_idx4; a.next_base = ls.base + id; a.next_count = b->count3() + id; }   // GOTOH overflow -> TRUNC
                 a.wide_idx = b->d_idx3 + (size_t)kind * nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + kind;
+                if (cls == 1) { const int rc = chunk_launch(a, kind, K); if (rc != SSW_OK) return rc; }
                 CU_TRY(launch_score(K, kind == 1, false, a, b->sblocks[cls], st));
                 ++launches;
             }
@@ -368,6 +440,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
             a.wl = WorkList{b->d_idx4, ls.base + id, b->count3() + id, b->cursor3() + id};
             a.rerun = 1;
             a.wide_idx = b->d_idx3 + nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + 1;
+            if (cls == 1) { const int rc = chunk_launch(a, 0, K); if (rc != SSW_OK) return rc; }      // the GOTOH-first pairs of this K
             CU_TRY(launch_score(K, true, false, a, b->sblocks[cls], st));
             ++launches;
         }
@@ -379,6 +452,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
             ScoreArgs a = score_args(cls);
             a.wl = WorkList{b->d_idx2, ls.base + id, b->count2() + id, b->cursor2() + id};
             a.rerun = 1;
+            if (cls == 1) { const int rc = chunk_launch(a, 1, K); if (rc != SSW_OK) return rc; }      // the TRUNC-first pairs of this K
             CU_TRY(launch_score(K, false, false, a, b->sblocks[cls], st));
             ++launches;
         }
@@ -562,8 +636,13 @@ extern "C" int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, 
     if (const char* e = getenv("SSW_CUDA_CHUNK")) { const long v = atol(e); if (v > 0 && v < (1L << 30)) chunk = (int32_t)v; }
     if (cigar_used) *cigar_used = 0;
     if (n_pairs <= 0) return n_pairs == 0 ? SSW_OK : SSW_ERR_ARG;
-    ssw_batch* slot[2] = {nullptr, nullptr};
-    int32_t slot_p0[2] = {0, 0};
+    // chunks in flight: while the host waits for the oldest one, the kernels of the younger ones keep the
+    // SMs busy through each other's launch tails and their uploads overlap
+    constexpr int MAX_SLOTS = 4;
+    int slots = 3;
+    if (const char* e = getenv("SSW_CUDA_SLOTS")) { const long v = atol(e); if (v >= 2 && v <= MAX_SLOTS) slots = (int)v; }
+    ssw_batch* slot[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t slot_p0[MAX_SLOTS] = {0, 0, 0, 0};
     int64_t cig_base = 0;
     int rc = SSW_OK;
     auto finish = [&](int sidx) -> int {
@@ -583,17 +662,17 @@ extern "C" int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, 
     int k = 0;
     for (int32_t p0 = 0; p0 < n_pairs && rc == SSW_OK; p0 += chunk, ++k) {
         const int32_t cnt = std::min<int32_t>(chunk, n_pairs - p0);
-        const int sidx = k & 1;
+        const int sidx = k % slots;
         ssw_batch* b = ssw_batch_create(device, nullptr, cnt, seqs, seqs_len, q_off + p0, q_len + p0, r_off + p0, r_len + p0,
                                         mask_len ? mask_len + p0 : nullptr, scoring);
         if (!b) { rc = error_code_of_create(); break; }
         slot[sidx] = b; slot_p0[sidx] = p0;
         rc = ssw_batch_run(b);
         if (rc != SSW_OK) break;
-        rc = finish(sidx ^ 1);                      // the previous chunk: its kernels ran while this one was uploaded
+        rc = finish((k + 1) % slots);               // the oldest chunk in flight (results stay in pair order)
     }
-    if (rc == SSW_OK && k > 0) rc = finish((k - 1) & 1);       // the last chunk
-    for (int sidx = 0; sidx < 2; ++sidx) if (slot[sidx]) { ssw_batch_destroy(slot[sidx]); slot[sidx] = nullptr; }
+    for (int j = 1; j <= slots && rc == SSW_OK; ++j) rc = finish((k + j) % slots);      // drain, oldest first
+    for (int sidx = 0; sidx < MAX_SLOTS; ++sidx) if (slot[sidx]) { ssw_batch_destroy(slot[sidx]); slot[sidx] = nullptr; }
     if (rc == SSW_OK && cigar_used) *cigar_used = cig_base;
     return rc;
 }

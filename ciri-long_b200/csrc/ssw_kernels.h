@@ -5,6 +5,34 @@
 namespace sswb {
 
 // ---- score passes (ssw_score.cu)
+// ---- long references: the forward pass over column chunks
+// A zero-started pass over columns [c0 - ov, c1) gives the exact H values of columns [c0, c1) when
+// ov > m * (1 + maxMatch / gap_extend): a path that starts before the overlap has crossed more than ov
+// columns, which costs at least (ov - m) * gap_extend in horizontal gaps against at most m * maxMatch gained,
+// so its score is negative and it cannot set any H (floor 0).  Every chunk is an independent task; the
+// tasks of a pair merge their best cell with an atomic max and write their columns of the pair's
+// column records, the last one to finish runs the pair's epilogue.
+struct ChunkPlan {
+    int32_t chunk_cols;            // 0 = whole pairs
+    int32_t max_match;
+    int32_t* task_pair;            // task tables of this launch
+    int32_t* task_c0;
+    int32_t* task_c1;
+    unsigned long long* pair_key;  // per pair: (score, first column, row) of the best cell so far
+    int32_t* pair_left;            // per pair: tasks still running
+    const int64_t* col_off;        // per pair: offset of its column records in col_pool
+    unsigned* col_pool;
+};
+__host__ __device__ inline int chunk_overlap(int m, int maxMatch, int ge) { return m * (1 + (maxMatch + ge - 1) / ge) + 2; }
+// number of tasks of a pair; 1 = the whole pair (queries of more than one tile, short references, or an
+// overlap that would eat the gain)
+__host__ __device__ inline int chunk_tasks(int m, int n, int chunk_cols, int maxMatch, int ge)
+{
+    if (chunk_cols <= 0 || m > VSTRIPS * KMAX || n <= chunk_cols || n >= (1 << 28)) return 1;
+    if (4LL * (chunk_overlap(m, maxMatch, ge) + RP_CHUNK) > chunk_cols) return 1;
+    return (n + chunk_cols - 1) / chunk_cols;
+}
+
 struct ScoreArgs {
     BatchView b;
     Scoring sc;
@@ -18,6 +46,7 @@ struct ScoreArgs {
     int32_t* next_count;
     int32_t* wide_idx;             // forward only: pairs handed to the 32-bit kernels (ssw_score32.cu)
     int32_t* wide_count;
+    ChunkPlan ck;                  // forward only: long references cut into column chunks (chunk_cols > 0)
 };
 
 // bytes of scratch one warp needs for references of up to n_cap columns
@@ -71,6 +100,9 @@ struct ListSet {
 cudaError_t build_lists(int stage, const BatchView& b, const Scoring& sc, int long_ref_threshold,
                         const ListSet& ls, cudaStream_t st, int* launches);
 // all pairs that still need the CIGAR pass, in one list (count at ls.count[0])
+// long references: expand the pairs of a forward list into column-chunk tasks
+cudaError_t expand_tasks(const WorkList& wl, int max_pairs, const BatchView& b, const Scoring& sc, const ChunkPlan& ck,
+                         int32_t* task_count, cudaStream_t st, int* launches);
 cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet& ls, cudaStream_t st, int* launches);
 
 // clear status bits (and the CIGAR window) of every pair, e.g. before the CIGAR pass is repeated

@@ -140,6 +140,34 @@ cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet
     return cudaGetLastError();
 }
 
+// ---- long references: one task per column chunk (ssw_kernels.h: ChunkPlan)
+__global__ void expand_tasks_kernel(WorkList wl, BatchView b, Scoring sc, ChunkPlan ck, int32_t* task_count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *wl.count) return;
+    const int pair = wl.idx[(wl.base ? *wl.base : 0) + i];
+    const int m = b.q_len[pair], n = b.r_len[pair];
+    const int nt = chunk_tasks(m, n, ck.chunk_cols, ck.max_match, sc.ge);
+    const int at = atomicAdd(task_count, nt);
+    for (int t = 0; t < nt; ++t) {
+        const int c0 = nt == 1 ? 0 : t * ck.chunk_cols;
+        ck.task_pair[at + t] = pair;
+        ck.task_c0[at + t] = c0;
+        ck.task_c1[at + t] = (nt == 1 || c0 + ck.chunk_cols > n) ? n : c0 + ck.chunk_cols;
+    }
+    ck.pair_left[pair] = nt;
+    ck.pair_key[pair] = 0ull;
+}
+
+cudaError_t expand_tasks(const WorkList& wl, int max_pairs, const BatchView& b, const Scoring& sc, const ChunkPlan& ck,
+                         int32_t* task_count, cudaStream_t st, int* launches)
+{
+    if (max_pairs <= 0) return cudaSuccess;
+    expand_tasks_kernel<<<(max_pairs + 255) / 256, 256, 0, st>>>(wl, b, sc, ck, task_count);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 __global__ void clear_status_kernel(BatchView b, int bits)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

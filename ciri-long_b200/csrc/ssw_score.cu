@@ -58,8 +58,9 @@ __device__ __forceinline__ StripGeom strip_geom(int v, int Vtot, int dead, int s
     return s;
 }
 
-template <int K, bool TRUNC, bool REV>
-__device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, const unsigned* lut, unsigned char* rpw, unsigned char* ws)
+template <int K, bool TRUNC, bool REV, bool CHUNK>
+__device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, const unsigned* lut, unsigned char* rpw, unsigned char* ws,
+                                           const int c0 = -1, const int c1 = 0)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
@@ -108,6 +109,30 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             if (lane == 0) rec->status |= PS_PUNT;
             return;
         }
+    }
+
+    // ---- forward pass over one column chunk of a long reference (ssw_kernels.h: ChunkPlan): the wavefront
+    // runs over columns [cw, c1) of the reference; columns before c0 = cw + skip only warm the state up.
+    // The few values this needs later (skip, cw, whether the task is the whole pair) wait in the spare bytes
+    // of the warp's shared-memory window instead of registers that the inner loop has no room for.
+    int* const ckw = reinterpret_cast<int*>(rpw + RP_WINDOW - 12);
+    if (CHUNK) {
+        int cw = 0, skip = 0;
+        if (c0 >= 0) {
+            if (c0 > 0) {
+                // the writer strip (63: chunks are cut only for single-tile queries) reaches column `skip` at step
+                // skip + 63; skip is a multiple of RP_CHUNK so that this is a border of the sweep's blocks
+                const int ov = chunk_overlap(m, a.ck.max_match, ge);
+                skip = ((ov + RP_CHUNK - 1) / RP_CHUNK) * RP_CHUNK;
+                cw = c0 - skip;
+                if (cw <= 0) { cw = 0; skip = 0; }                  // exact from column 0: duplicates of the first chunk's work are harmless
+            }
+            rb += cw;
+            const int whole = (c0 == 0 && c1 == n) ? 1 : 0;
+            n = c1 - cw;
+            if (lane == 0) { ckw[0] = skip; ckw[1] = cw; ckw[2] = whole; }
+        } else if (lane == 0) { ckw[0] = 0; ckw[1] = 0; ckw[2] = 1; }
+        __syncwarp();
     }
 
     const unsigned GO = pack2(go, go);                              // bias of every stored score, and the local floor
@@ -249,19 +274,25 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             bool pHi, pLo;
             const unsigned nb = __vibmax_s16x2(bestT, mxv, &pHi, &pLo);  // pred = (bestT >= mxv)
             if (!(pHi && pLo)) {
-                if (!pLo) {
+                // (chunk mode: warm-up columns, c < skip, are not recorded and do not raise the threshold)
+                const int skip = CHUNK ? ckw[0] : 0;
+                unsigned acc = 0;
+                if (!pLo && (!CHUNK || cLo >= skip)) {
                     best = (best & 0xffff0000u) | (mxv & 0xffffu);
                     bcolLo = cLo;
+                    acc = 0xffffu;
 #pragma unroll
                     for (int i = 0; i < K; ++i) snap[i * 32 + lane] = Hd[i];
                 }
-                if (!pHi) {
+                if (!pHi && (!CHUNK || cHi >= skip)) {
                     best = (best & 0xffffu) | (mxv & 0xffff0000u);
                     bcolHi = cHi;
+                    acc |= 0xffff0000u;
 #pragma unroll
                     for (int i = 0; i < K; ++i) snap[(K + i) * 32 + lane] = Hd[i];
                 }
-                bestT = nb;
+                if (!CHUNK) bestT = nb;
+                else bestT = (nb & acc) | (bestT & ~acc);
             }
             // the complete column leaves the tile at the writer strip
             const unsigned wval = __byte_perm(R, Hout, selW);               // colmax | H(last row) << 16 of the writer's half
@@ -295,6 +326,12 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 if (s0 < sA) { if (s1 > sA) s1 = sA; }
                 else if (s0 < sB) { if (s1 > sB) s1 = sB; }
                 const bool steady = s0 >= sA && s1 <= sB;
+                if (CHUNK) {
+                    // column records of the chunk's own columns go to the pair's array, warm-up columns to scratch
+                    const int skip = ckw[0];
+                    const bool own = skip == 0 || s0 >= skip + wv;
+                    wcol = (own ? a.ck.col_pool + a.ck.col_off[pair] + ckw[1] : colbuf) - wv;
+                }
                 __syncwarp();
                 for (int x = lane; x < s1 - s0 + 32; x += 32) {
                     const int c = s0 - 31 + x, c2 = c - 32;
@@ -359,6 +396,33 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
     break;
     }
 
+    if (CHUNK) {
+        if (candM > 0) candCol += ckw[1];
+        if (!ckw[2]) {
+            // merge with the pair's other chunks: largest score, then first column (one task owns a column, so
+            // the row comes with it); the task that finishes last carries on with the pair's epilogue
+            unsigned long long key = candM > 0 ? ((unsigned long long)candM << 49) |
+                                                 ((unsigned long long)(0xfffffff - candCol) << 21) | (unsigned long long)candRow : 0ull;
+            int left = 0;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                if (key) atomicMax(a.ck.pair_key + pair, key);
+                __threadfence();
+                left = atomicSub(a.ck.pair_left + pair, 1) - 1;
+            }
+            left = __shfl_sync(FULL, left, 0);
+            if (left > 0) return;
+            __threadfence();
+            key = *reinterpret_cast<volatile unsigned long long*>(a.ck.pair_key + pair);
+            candM = (int)(key >> 49);
+            candCol = candM > 0 ? 0xfffffff - (int)((key >> 21) & 0xfffffffull) : -1;
+            candRow = candM > 0 ? (int)(key & 0x1fffffull) : 0;
+        }
+        n = a.b.r_len[pair];
+        colbuf = a.ck.col_pool + a.ck.col_off[pair];
+    }
+
     if (!REV) {
         const bool over8 = candM + a.sc.bias >= 255;               // ssw.c:285,317
         int word = TRUNC ? 1 : (over8 ? 1 : 0);
@@ -420,7 +484,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
     }
 }
 
-template <int K, bool TRUNC, bool REV>
+template <int K, bool TRUNC, bool REV, bool CHUNK>
 __global__ void __launch_bounds__(score_warps(K) * 32, 1) score_kernel(const ScoreArgs a)
 {
     extern __shared__ unsigned lut[];
@@ -444,7 +508,10 @@ __global__ void __launch_bounds__(score_warps(K) * 32, 1) score_kernel(const Sco
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        score_pair<K, TRUNC, REV>(a, a.wl.idx[base + idx], lut, rpw, ws);
+        int pair, c0 = -1, c1 = 0;
+        if (CHUNK) { pair = a.ck.task_pair[idx]; c0 = a.ck.task_c0[idx]; c1 = a.ck.task_c1[idx]; }
+        else pair = a.wl.idx[base + idx];
+        score_pair<K, TRUNC, REV, CHUNK>(a, pair, lut, rpw, ws, c0, c1);
         __syncwarp();
     }
 }
@@ -452,26 +519,30 @@ __global__ void __launch_bounds__(score_warps(K) * 32, 1) score_kernel(const Sco
 // ---------------------------------------------------------------------------------------------------
 // host-side launch table
 
-template <int K, bool TRUNC, bool REV>
+template <int K, bool TRUNC, bool REV, bool CHUNK>
 static cudaError_t launch_one(const ScoreArgs& a, int blocks, cudaStream_t st)
 {
     static bool configured[16] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(score_kernel<K, TRUNC, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCORE_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(score_kernel<K, TRUNC, REV, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCORE_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    score_kernel<K, TRUNC, REV><<<blocks, score_warps(K) * 32, SCORE_SMEM_BYTES, st>>>(a);
+    score_kernel<K, TRUNC, REV, CHUNK><<<blocks, score_warps(K) * 32, SCORE_SMEM_BYTES, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int K>
 static cudaError_t launch_k(const ScoreArgs& a, bool trunc, bool rev, int blocks, cudaStream_t st)
 {
-    if (trunc) return rev ? launch_one<K, true, true>(a, blocks, st) : launch_one<K, true, false>(a, blocks, st);
-    return rev ? launch_one<K, false, true>(a, blocks, st) : launch_one<K, false, false>(a, blocks, st);
+    // chunk mode (ScoreArgs::ck) exists for the forward pass only and has its own instances, so that the
+    // common whole-pair kernels carry none of its code
+    if (!rev && a.ck.chunk_cols)
+        return trunc ? launch_one<K, true, false, true>(a, blocks, st) : launch_one<K, false, false, true>(a, blocks, st);
+    if (trunc) return rev ? launch_one<K, true, true, false>(a, blocks, st) : launch_one<K, true, false, false>(a, blocks, st);
+    return rev ? launch_one<K, false, true, false>(a, blocks, st) : launch_one<K, false, false, false>(a, blocks, st);
 }
 
 cudaError_t launch_score(int K, bool trunc, bool rev, const ScoreArgs& a, int blocks, cudaStream_t st)

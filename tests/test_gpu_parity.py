@@ -319,6 +319,33 @@ def test_batched_collapse_call_sites(sw, oracle):
     assert cs.exon_scores_batch(cons, []) == []
 
 
+def test_long_references_in_column_chunks(sw, oracle):
+    """find_bsj window shape (find_bsj.py:182-233): short queries against references of tens to hundreds of
+    kilobases.  The forward pass runs as column-chunk tasks (ChunkPlan); every field incl. the second-best
+    score (which reads the merged column records) and the CIGAR must come out as for whole pairs"""
+    from ciri_long_b200 import workloads as W
+    rng = np.random.default_rng(123)
+    for params in ((1, 1, 1, 1), (10, 4, 8, 2)):
+        qs, rs = [], []
+        for k in range(14):
+            n = int(rng.integers(33000, 140000))
+            r = rng.integers(0, 4, n).astype(np.int8)
+            m = int((20, 60, 150, 300, 340, 420, 500, 700, 1000, 1100, 1500, 250, 480, 90)[k])
+            st = int(rng.integers(0, n - m))
+            q, _ = W.noisy_channel(r[st:st + m].copy(), np.array([m]), rng, n_frac=0.01)
+            if k % 5 == 0:                                            # a second, weaker copy far away: score2 / ref_end2
+                st2 = (st + n // 2) % (n - m)
+                q2, _ = W.noisy_channel(q.copy(), np.array([len(q)]), rng, sub=0.15)
+                r = r.copy(); r[st2:st2 + min(len(q2), n - st2)] = q2[:min(len(q2), n - st2)]
+            if k == 3:                                                # alignment across a chunk border
+                st = 8192 * 4 - m // 2
+                q, _ = W.noisy_channel(r[st:st + m].copy(), np.array([m]), rng)
+            qs.append(q); rs.append(r)
+        qs.append(rng.integers(0, 4, 200).astype(np.int8)); rs.append(rng.integers(0, 4, 70000).astype(np.int8))   # unrelated
+        b = W.from_lists(qs, rs, params, name="long-ref %s" % (params,))
+        check_batch(sw, oracle, b)
+
+
 def test_mixed_length_batch(sw, oracle):
     """C5-style mixture under one scoring scheme: tiny junction pairs, read-vs-read segments, long reads vs
     50-nt junctions, shuffled into one batch (every kernel instance and list class at once)"""
