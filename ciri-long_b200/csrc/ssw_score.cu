@@ -58,11 +58,29 @@ __device__ __forceinline__ StripGeom strip_geom(int v, int Vtot, int dead, int s
     return s;
 }
 
+// A strip's H column at the step of a new maximum, K words per (half, lane), written as 16-byte vectors:
+// the store is executed by the whole warp for one active lane, so fewer, wider stores are cheaper.
+template <int K>
+__device__ __forceinline__ void store_snapshot(unsigned* dst, const unsigned (&Hd)[K])
+{
+    constexpr int KP = (K + 3) & ~3;
+#pragma unroll
+    for (int i = 0; i < KP; i += 4) {
+        uint4 v;
+        v.x = Hd[i];
+        v.y = i + 1 < K ? Hd[i + 1] : 0u;
+        v.z = i + 2 < K ? Hd[i + 2] : 0u;
+        v.w = i + 3 < K ? Hd[i + 3] : 0u;
+        *reinterpret_cast<uint4*>(dst + i) = v;
+    }
+}
+
 template <int K, bool TRUNC, bool REV, bool CHUNK>
 __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, const unsigned* lut, unsigned char* rpw, unsigned char* ws,
                                            const int c0 = -1, const int c1 = 0)
 {
     const unsigned FULL = 0xffffffffu;
+    constexpr int KP = (K + 3) & ~3;                                // words per snapshot
     const int lane = lane_id();
     PairRec* rec = a.b.rec + pair;
 
@@ -281,15 +299,13 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                     best = (best & 0xffff0000u) | (mxv & 0xffffu);
                     bcolLo = cLo;
                     acc = 0xffffu;
-#pragma unroll
-                    for (int i = 0; i < K; ++i) snap[i * 32 + lane] = Hd[i];
+                    store_snapshot<K>(snap + lane * KP, Hd);
                 }
                 if (!pHi && (!CHUNK || cHi >= skip)) {
                     best = (best & 0xffffu) | (mxv & 0xffff0000u);
                     bcolHi = cHi;
                     acc |= 0xffff0000u;
-#pragma unroll
-                    for (int i = 0; i < K; ++i) snap[(K + i) * 32 + lane] = Hd[i];
+                    store_snapshot<K>(snap + (32 + lane) * KP, Hd);
                 }
                 if (!CHUNK) bestT = nb;
                 else bestT = (nb & acc) | (bestT & ~acc);
@@ -374,7 +390,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             if (lane == owner) {
                 const StripGeom sg = half ? sHi : sLo;
                 for (int i = sg.live - 1; i >= 0; --i) {
-                    const unsigned v = snap[(half * K + i) * 32 + lane];
+                    const unsigned v = snap[(half * 32 + lane) * KP + i];
                     if ((half ? hi16(v) : lo16(v)) - go == M) row = sg.first + i;
                 }
                 if (row > m - 1) row = m - 1;                           // pad rows never lower end_read (ssw.c:144,306)
