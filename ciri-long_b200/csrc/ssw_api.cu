@@ -343,8 +343,8 @@ extern "C" ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs
     return b;
 }
 
-// CIGAR pass: list of pairs that pass the reference's gate (ssw.c:850), narrow instance, then the wide
-// instance for the pairs the narrow one handed over.
+// CIGAR pass: list of pairs that pass the reference's gate (ssw.c:850), narrow instance, then the two
+// wider instances for the pairs handed over.
 static int enqueue_cigar_stage(ssw_batch* b, int* launches)
 {
     cudaStream_t st = b->stream;
@@ -358,12 +358,18 @@ static int enqueue_cigar_stage(ssw_batch* b, int* launches)
     ba.scratch = b->d_bscr; ba.scratch_stride = b->bstride; ba.dir_bytes = b->bdir;
     ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap;
     ba.cigar_used = b->d_cigar_used;
+    // class 0 hands bands of 129-256 diagonals to class 1 (list in d_idx2) and anything wider to class 2
+    // (list in d_idx4); class 1 hands on to class 2 as well
     ba.next_idx = b->d_idx2; ba.next_count = b->count2();
-    CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
-    CU_TRY(launch_band(false, ba, b->bblocks, st));
-    ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+    ba.next2_idx = b->d_idx4; ba.next2_count = b->count3();
+    CU_TRY(cudaMemsetAsync(b->count2(), 0, 4 * N_LISTS * 4, st));       // count2, cursor2, count3, cursor3
+    CU_TRY(launch_band(0, ba, b->bblocks, st));
     ba.scratch = b->d_wscr; ba.scratch_stride = b->wstride; ba.dir_bytes = b->wdir;
-    CU_TRY(launch_band(true, ba, b->wblocks, st));
+    ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+    CU_TRY(launch_band(1, ba, b->wblocks, st));
+    ba.wl = WorkList{b->d_idx4, nullptr, b->count3(), b->cursor3()};
+    CU_TRY(launch_band(2, ba, b->wblocks, st));
+    *launches += 1;
     *launches += 2;
     return SSW_OK;
 }
@@ -543,10 +549,14 @@ static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
     ba.scratch = scr; ba.scratch_stride = stride; ba.dir_bytes = need;
     ba.cigar_stage_cap = b->bstage; ba.cigar_buf = b->d_cigar; ba.cigar_cap = b->cigar_cap; ba.cigar_used = b->d_cigar_used;
     ba.next_idx = b->d_idx2; ba.next_count = b->count2();
-    CU_TRY(cudaMemsetAsync(b->count2(), 0, 2 * N_LISTS * 4, st));
-    CU_TRY(launch_band(false, ba, blocks, st));
+    ba.next2_idx = b->d_idx4; ba.next2_count = b->count3();
+    CU_TRY(cudaMemsetAsync(b->count2(), 0, 4 * N_LISTS * 4, st));
+    CU_TRY(launch_band(0, ba, blocks, st));
     ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
-    CU_TRY(launch_band(true, ba, blocks, st));
+    CU_TRY(launch_band(1, ba, blocks, st));
+    ba.wl = WorkList{b->d_idx4, nullptr, b->count3(), b->cursor3()};
+    CU_TRY(launch_band(2, ba, blocks, st));
+    b->launches += 1;
     b->launches += 2;
     for (int32_t p : big)
         CU_TRY(cudaMemcpyAsync(&b->h_rec[p], &b->d_rec[p], sizeof(PairRec), cudaMemcpyDeviceToHost, st));

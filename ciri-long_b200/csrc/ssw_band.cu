@@ -252,10 +252,11 @@ __device__ int band_fill_scan(const BandJob& jb, int* Hrow, unsigned char* dir, 
     return __reduce_max_sync(FULL, maxv);
 }
 
-// WIDE = false: bands of up to 128 diagonals (the common case, few registers); a pair whose band grows
-// past that is handed to the WIDE instance (its own launch) together with the band width reached and the
+// CLASS 0: bands of up to 128 diagonals (the common case, 64 registers); CLASS 1: up to 256 (8 diagonals per
+// lane, 128 registers); CLASS 2: everything wider (255 registers).  A pair whose band grows past its class
+// is handed to the next instance (its own launch) together with the band width reached and the
 // running maximum, which is all the doubling loop carries from one width to the next (ssw.c:571-632).
-template <bool WIDE>
+template <int CLASS>
 __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, unsigned char* win, const uint2* stab)
 {
     const unsigned FULL = 0xffffffffu;
@@ -284,7 +285,7 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
         const int readLen = jb.readLen, refLen = jb.refLen;
         int bw = refLen - readLen; if (bw < 0) bw = -bw; bw += 1;
         int maxv = 0, rowStride = 0, dpl = 0;
-        if (WIDE) { bw = -rec->cigar_len; maxv = (int)rec->cigar_off; }
+        if (CLASS > 0) { bw = -rec->cigar_len; maxv = (int)rec->cigar_off; }
         unsigned char* dir = nullptr;
         for (;;) {
             const int Wd = 2 * bw + 1;
@@ -294,10 +295,11 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
             int P = 0;
             if (Wd <= 64) P = 2; else if (Wd <= 96) P = 3; else if (Wd <= 128) P = 4;
             else if (Wd <= 256) P = 8; else if (Wd <= 512) P = 16; else if (Wd <= 1024) P = 32;
-            if (!WIDE && (P == 0 || P > 4)) {
+            if ((CLASS == 0 && (P == 0 || P > 4)) || (CLASS == 1 && (P == 0 || P > 8))) {
                 if (lane == 0) {
                     rec->cigar_len = -bw; rec->cigar_off = maxv;
-                    a.next_idx[atomicAdd(a.next_count, 1)] = pair;
+                    if (CLASS == 0 && P == 8) a.next_idx[atomicAdd(a.next_count, 1)] = pair;
+                    else a.next2_idx[atomicAdd(a.next2_count, 1)] = pair;
                 }
                 return;
             }
@@ -311,11 +313,18 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
             const bool q = 2 * bw + 1 >= refLen - 1;
 #define SSW_WAVE(PP) (q ? band_fill_wave<PP, true>(jb.ref, jb.read, refLen, readLen, bw, jb.go, jb.ge, stab, dir, rowStride, maxv) \
                         : band_fill_wave<PP, false>(jb.ref, jb.read, refLen, readLen, bw, jb.go, jb.ge, stab, dir, rowStride, maxv))
-            if (!WIDE) {
+            if (CLASS == 0) {
                 switch (P) {
                     case 2: maxv = SSW_WAVE(2); break;
                     case 3: maxv = SSW_WAVE(3); break;
                     default: maxv = SSW_WAVE(4); break;
+                }
+            } else if (CLASS == 1) {
+                switch (P) {                                     // (a pair can arrive with its band already at 8 per lane only)
+                    case 2: maxv = SSW_WAVE(2); break;
+                    case 3: maxv = SSW_WAVE(3); break;
+                    case 4: maxv = SSW_WAVE(4); break;
+                    default: maxv = SSW_WAVE(8); break;
                 }
             } else {
                 switch (P) {
@@ -408,8 +417,8 @@ __device__ void band_pair(const BandArgs& a, const int pair, unsigned char* ws, 
     }
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(BAND_WARPS * 32, WIDE ? 1 : 4) band_kernel(const BandArgs a)
+template <int CLASS>
+__global__ void __launch_bounds__(BAND_WARPS * 32, CLASS == 0 ? 4 : CLASS == 1 ? 2 : 1) band_kernel(const BandArgs a)
 {
     __shared__ uint4 window[BAND_WARPS][TB_WINDOW / 16];
     __shared__ uint2 stab[8];
@@ -431,15 +440,16 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, WIDE ? 1 : 4) band_kernel(con
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        band_pair<WIDE>(a, a.wl.idx[base + idx], ws, reinterpret_cast<unsigned char*>(window[warp]), stab);
+        band_pair<CLASS>(a, a.wl.idx[base + idx], ws, reinterpret_cast<unsigned char*>(window[warp]), stab);
         __syncwarp();
     }
 }
 
-cudaError_t launch_band(bool wide, const BandArgs& a, int blocks, cudaStream_t st)
+cudaError_t launch_band(int cls, const BandArgs& a, int blocks, cudaStream_t st)
 {
-    if (wide) band_kernel<true><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
-    else band_kernel<false><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
+    if (cls == 0) band_kernel<0><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
+    else if (cls == 1) band_kernel<1><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
+    else band_kernel<2><<<blocks, BAND_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -120,12 +120,14 @@ struct BandArgs {
     uint32_t* cigar_buf;           // device output buffer
     long long cigar_cap;
     unsigned long long* cigar_used;
-    int32_t* next_idx;             // narrow instance: pairs handed to the wide instance
+    int32_t* next_idx;             // class 0: pairs handed to class 1 (bands of 129-256 diagonals)
     int32_t* next_count;
+    int32_t* next2_idx;            // class 0 and 1: pairs handed to class 2
+    int32_t* next2_count;
 };
 constexpr int BAND_WARPS = 8;
-// wide = false: bands up to 128 diagonals; wide = true: everything the narrow launch handed over
-cudaError_t launch_band(bool wide, const BandArgs& a, int blocks, cudaStream_t st);
+// cls 0: bands up to 128 diagonals; 1: up to 256; 2: everything the others handed over
+cudaError_t launch_band(int cls, const BandArgs& a, int blocks, cudaStream_t st);
 
 // ---- batched edit distance (edit_distance.cu)
 constexpr int ED_MAXSYM = 16;          // distinct symbols per batch (4-bit codes)
