@@ -113,6 +113,10 @@ struct ssw_batch {
     int32_t* d_task = nullptr;           // task_pair | task_c0 | task_c1, each task_total entries
     long long task_total = 0;
     int32_t* d_task_meta = nullptr;      // counts[2][KMAX+1] | cursors[2][KMAX+1]
+    int32_t* d_rtask = nullptr;          // reverse pass: task tables (one list at a time) and per-task results
+    int4* d_rres = nullptr;
+    long long rev_task_total = 0;
+    int32_t long_total = 0;              // class-1 pairs in the batch
     int64_t launches = 0;
     std::vector<PairRec> h_rec;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last run
@@ -152,7 +156,7 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     dev_free(b->d_seqs, fs); dev_free(b->d_qoff, fs); dev_free(b->d_roff, fs); dev_free(b->d_qlen, fs); dev_free(b->d_rlen, fs);
     dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_idx4, fs); dev_free(b->d_meta, fs);
     dev_free(b->d_col_off, fs); dev_free(b->d_col_pool, fs); dev_free(b->d_pair_key, fs); dev_free(b->d_pair_left, fs);
-    dev_free(b->d_task, fs); dev_free(b->d_task_meta, fs);
+    dev_free(b->d_task, fs); dev_free(b->d_task_meta, fs); dev_free(b->d_rtask, fs); dev_free(b->d_rres, fs);
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
@@ -206,6 +210,8 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
                 b->long_pairs[kind][K] += 1;
                 b->task_cap[kind][K] += chunk_tasks(m, r, b->chunk_cols, maxScore, b->sc.ge);
                 h_col_off[p] = col_total;
+                b->long_total += 1;
+                b->rev_task_total += (r + b->chunk_cols - 1) / b->chunk_cols + 1;
                 col_total += ((long long)r + 31) & ~31LL;             // 128-byte aligned: no cache line is shared by two pairs
             }
             if (kind == 0 && b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255)
@@ -252,6 +258,10 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         CU_TRY(dev_alloc_t(&b->d_pair_left, nn, st));
         CU_TRY(dev_alloc_t(&b->d_task, (size_t)(3 * b->task_total + 16), st));
         CU_TRY(dev_alloc_t(&b->d_task_meta, 4 * (KMAX + 1), st));
+        if (b->sc.flag != 0) {
+            CU_TRY(dev_alloc_t(&b->d_rtask, (size_t)(3 * b->rev_task_total + 16), st));
+            CU_TRY(dev_alloc_t(&b->d_rres, (size_t)(b->rev_task_total + 16), st));
+        }
         // (the vector dies with this function: the copy is made from a staging allocation that outlives it)
         b->h_col_off.swap(h_col_off);
         CU_TRY(cudaMemcpyAsync(b->d_col_off, b->h_col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -413,7 +423,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         a.ck.task_c1 = b->d_task + 2 * b->task_total + b->task_base[kind][K];
         a.ck.pair_key = b->d_pair_key; a.ck.pair_left = b->d_pair_left;
         a.ck.col_off = b->d_col_off; a.ck.col_pool = b->d_col_pool;
-        CU_TRY(expand_tasks(a.wl, b->long_pairs[kind][K], view, b->sc, a.ck, cnt, st, &launches));
+        CU_TRY(expand_tasks(a.wl, b->long_pairs[kind][K], false, view, b->sc, a.ck, cnt, st, &launches));
         a.wl = WorkList{nullptr, nullptr, cnt, cur};
         return SSW_OK;
     };
@@ -474,6 +484,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
     if (b->sc.flag != 0) {
         // ---- reverse pass: strip height follows the read prefix, so any K up to the forward maximum can occur
         CU_TRY(build_lists(1, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
+        if (b->chunk_cols) CU_TRY(cudaMemsetAsync(b->count3(), 0, 2 * N_LISTS * 4, st));
         for (int cls = 0; cls < 2; ++cls) {
             if (!b->d_sscr[cls]) continue;
             for (int kind = 0; kind < 2; ++kind) {
@@ -482,6 +493,27 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                     const int id = list_id(cls, kind, K);
                     ScoreArgs a = score_args(cls);
                     a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
+                    if (cls == 1 && b->chunk_cols) {
+                        // long references: a bounded first look for the stop column; pairs without one go to a list
+                        // (same partition of d_idx4) and are expanded into column-chunk tasks over the whole prefix
+                        a.ck.chunk_cols = b->chunk_cols; a.ck.max_match = maxScore;
+                        a.next_idx = b->d_idx4; a.next_base = ls.base + id; a.next_count = b->count3() + id;
+                        CU_TRY(launch_score(K, kind == 1, true, a, b->sblocks[cls], st));
+                        int32_t* cnt = b->d_task_meta + kind * (KMAX + 1) + K;
+                        int32_t* cur = b->d_task_meta + 2 * (KMAX + 1) + kind * (KMAX + 1) + K;
+                        CU_TRY(cudaMemsetAsync(cnt, 0, 4, st));
+                        CU_TRY(cudaMemsetAsync(cur, 0, 4, st));
+                        ScoreArgs t = a;
+                        t.ck.task_pair = b->d_rtask; t.ck.task_c0 = b->d_rtask + b->rev_task_total;
+                        t.ck.task_c1 = b->d_rtask + 2 * b->rev_task_total; t.ck.task_res = b->d_rres;
+                        t.ck.pair_key = b->d_pair_key; t.ck.pair_left = b->d_pair_left;
+                        const WorkList longList{b->d_idx4, ls.base + id, b->count3() + id, nullptr};
+                        CU_TRY(expand_tasks(longList, b->long_total, true, view, b->sc, t.ck, cnt, st, &launches));
+                        t.wl = WorkList{nullptr, nullptr, cnt, cur};
+                        CU_TRY(launch_score(K, kind == 1, true, t, b->sblocks[cls], st));
+                        launches += 2;
+                        continue;
+                    }
                     CU_TRY(launch_score(K, kind == 1, true, a, b->sblocks[cls], st));
                     ++launches;
                 }

@@ -18,12 +18,16 @@ struct ChunkPlan {
     int32_t* task_pair;            // task tables of this launch
     int32_t* task_c0;
     int32_t* task_c1;
-    unsigned long long* pair_key;  // per pair: (score, first column, row) of the best cell so far
+    unsigned long long* pair_key;  // per pair, forward: (score, first column, row) of the best cell so far;
+                                   //           reverse: (first task << 32) | number of tasks
     int32_t* pair_left;            // per pair: tasks still running
     const int64_t* col_off;        // per pair: offset of its column records in col_pool
     unsigned* col_pool;
+    int4* task_res;                // reverse pass: per task (stop column, best score, its column, its row)
 };
 __host__ __device__ inline int chunk_overlap(int m, int maxMatch, int ge) { return m * (1 + (maxMatch + ge - 1) / ge) + 2; }
+// reverse pass: columns of the first, bounded look (the stop column is normally about one alignment away)
+__host__ __device__ inline int rev_look(int m) { return (2 * m + 1024 + RP_CHUNK - 1) / RP_CHUNK * RP_CHUNK; }
 // number of tasks of a pair; 1 = the whole pair (queries of more than one tile, short references, or an
 // overlap that would eat the gain)
 __host__ __device__ inline int chunk_tasks(int m, int n, int chunk_cols, int maxMatch, int ge)
@@ -101,7 +105,7 @@ cudaError_t build_lists(int stage, const BatchView& b, const Scoring& sc, int lo
                         const ListSet& ls, cudaStream_t st, int* launches);
 // all pairs that still need the CIGAR pass, in one list (count at ls.count[0])
 // long references: expand the pairs of a forward list into column-chunk tasks
-cudaError_t expand_tasks(const WorkList& wl, int max_pairs, const BatchView& b, const Scoring& sc, const ChunkPlan& ck,
+cudaError_t expand_tasks(const WorkList& wl, int max_pairs, bool rev, const BatchView& b, const Scoring& sc, const ChunkPlan& ck,
                          int32_t* task_count, cudaStream_t st, int* launches);
 cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet& ls, cudaStream_t st, int* launches);
 

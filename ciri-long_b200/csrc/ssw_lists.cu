@@ -141,12 +141,14 @@ cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet
 }
 
 // ---- long references: one task per column chunk (ssw_kernels.h: ChunkPlan)
-__global__ void expand_tasks_kernel(WorkList wl, BatchView b, Scoring sc, ChunkPlan ck, int32_t* task_count)
+__global__ void expand_tasks_kernel(WorkList wl, int rev, BatchView b, Scoring sc, ChunkPlan ck, int32_t* task_count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *wl.count) return;
     const int pair = wl.idx[(wl.base ? *wl.base : 0) + i];
-    const int m = b.q_len[pair], n = b.r_len[pair];
+    // forward: the whole pair; reverse: the prefix rectangle that ends at the forward pass's best cell
+    const int m = rev ? b.rec[pair].read_end1 + 1 : b.q_len[pair];
+    const int n = rev ? b.rec[pair].ref_end1 + 1 : b.r_len[pair];
     const int nt = chunk_tasks(m, n, ck.chunk_cols, ck.max_match, sc.ge);
     const int at = atomicAdd(task_count, nt);
     for (int t = 0; t < nt; ++t) {
@@ -156,14 +158,14 @@ __global__ void expand_tasks_kernel(WorkList wl, BatchView b, Scoring sc, ChunkP
         ck.task_c1[at + t] = (nt == 1 || c0 + ck.chunk_cols > n) ? n : c0 + ck.chunk_cols;
     }
     ck.pair_left[pair] = nt;
-    ck.pair_key[pair] = 0ull;
+    ck.pair_key[pair] = rev ? ((unsigned long long)at << 32) | (unsigned)nt : 0ull;
 }
 
-cudaError_t expand_tasks(const WorkList& wl, int max_pairs, const BatchView& b, const Scoring& sc, const ChunkPlan& ck,
+cudaError_t expand_tasks(const WorkList& wl, int max_pairs, bool rev, const BatchView& b, const Scoring& sc, const ChunkPlan& ck,
                          int32_t* task_count, cudaStream_t st, int* launches)
 {
     if (max_pairs <= 0) return cudaSuccess;
-    expand_tasks_kernel<<<(max_pairs + 255) / 256, 256, 0, st>>>(wl, b, sc, ck, task_count);
+    expand_tasks_kernel<<<(max_pairs + 255) / 256, 256, 0, st>>>(wl, rev ? 1 : 0, b, sc, ck, task_count);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -77,7 +77,7 @@ __device__ __forceinline__ void store_snapshot(unsigned* dst, const unsigned (&H
 
 template <int K, bool TRUNC, bool REV, bool CHUNK>
 __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, const unsigned* lut, unsigned char* rpw, unsigned char* ws,
-                                           const int c0 = -1, const int c1 = 0)
+                                           const int c0 = -1, const int c1 = 0, const int task = 0)
 {
     const unsigned FULL = 0xffffffffu;
     constexpr int KP = (K + 3) & ~3;                                // words per snapshot
@@ -134,6 +134,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
     // The few values this needs later (skip, cw, whether the task is the whole pair) wait in the spare bytes
     // of the warp's shared-memory window instead of registers that the inner loop has no room for.
     int* const ckw = reinterpret_cast<int*>(rpw + RP_WINDOW - 12);
+    bool limited = false;                                           // reverse pass: first look at a bounded number of columns
     if (CHUNK) {
         int cw = 0, skip = 0;
         if (c0 >= 0) {
@@ -145,11 +146,20 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 cw = c0 - skip;
                 if (cw <= 0) { cw = 0; skip = 0; }                  // exact from column 0: duplicates of the first chunk's work are harmless
             }
-            rb += cw;
+            rb += (long long)cw * rs;
             const int whole = (c0 == 0 && c1 == n) ? 1 : 0;
             n = c1 - cw;
             if (lane == 0) { ckw[0] = skip; ckw[1] = cw; ckw[2] = whole; }
-        } else if (lane == 0) { ckw[0] = 0; ckw[1] = 0; ckw[2] = 1; }
+        } else {
+            if (lane == 0) { ckw[0] = 0; ckw[1] = 0; ckw[2] = 1; }
+            if (REV) {
+                // Reverse pass of a long reference, first look: the stop column (ssw.c:296,499) normally lies about one
+                // alignment length away.  Only if it is not found within rev_look(m) columns is the pair expanded
+                // into column-chunk tasks over the whole prefix.
+                const int look = rev_look(m);
+                if (n > look && chunk_tasks(m, n, a.ck.chunk_cols, a.ck.max_match, ge) > 1) { n = look; limited = true; }
+            }
+        }
         __syncwarp();
     }
 
@@ -285,8 +295,9 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 //  value is dead and only the predicates are used)
                 const unsigned ov = addmax_relu(mxv, mtermP, 0u);              // max(mxv - score1, 0) per half
                 if (ov) {
-                    if (ov & 0xffffu) { overCol = cLo < overCol ? cLo : overCol; mxv &= 0xffff0000u; }
-                    if (ov >> 16) { overCol = cHi < overCol ? cHi : overCol; mxv &= 0x0000ffffu; }
+                    const int skipc = CHUNK ? ckw[0] : 0;               // (chunk mode: warm-up columns do not count)
+                    if (ov & 0xffffu) { if (!CHUNK || cLo >= skipc) overCol = cLo < overCol ? cLo : overCol; mxv &= 0xffff0000u; }
+                    if (ov >> 16) { if (!CHUNK || cHi >= skipc) overCol = cHi < overCol ? cHi : overCol; mxv &= 0x0000ffffu; }
                 }
             }
             bool pHi, pLo;
@@ -319,7 +330,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             } else if (!REV) {
                 if (colOk) wcol[s] = wval;
             } else if (colOk && !termflag && !exactMode && (int)(wval & 0xffffu) == terminate + go) {
-                termflag = 1; termCol = wHalf ? cHi : cLo;
+                if (!CHUNK || (wHalf ? cHi : cLo) >= ckw[0]) { termflag = 1; termCol = wHalf ? cHi : cLo; }
             }
             ++cLo; ++cHi;
         };
@@ -342,7 +353,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 if (s0 < sA) { if (s1 > sA) s1 = sA; }
                 else if (s0 < sB) { if (s1 > sB) s1 = sB; }
                 const bool steady = s0 >= sA && s1 <= sB;
-                if (CHUNK) {
+                if (CHUNK && !REV) {
                     // column records of the chunk's own columns go to the pair's array, warm-up columns to scratch
                     const int skip = ckw[0];
                     const bool own = skip == 0 || s0 >= skip + wv;
@@ -401,6 +412,10 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         if (lastTile) termCol = __shfl_sync(FULL, termCol, wLane);
         __syncwarp();      // boundary array / snapshots written by this tile are read by the next one
     }
+    if (CHUNK && REV && limited && termCol < 0) {
+        if (lane == 0) a.next_idx[*a.next_base + atomicAdd(a.next_count, 1)] = pair;
+        return;
+    }
     if (REV && !exactMode) {
         overCol = __reduce_min_sync(FULL, overCol);
         if (overCol != 0x7fffffff && (termCol < 0 || overCol <= termCol)) {
@@ -412,7 +427,7 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
     break;
     }
 
-    if (CHUNK) {
+    if (CHUNK && !REV) {
         if (candM > 0) candCol += ckw[1];
         if (!ckw[2]) {
             // merge with the pair's other chunks: largest score, then first column (one task owns a column, so
@@ -437,6 +452,32 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         }
         n = a.b.r_len[pair];
         colbuf = a.ck.col_pool + a.ck.col_off[pair];
+    }
+
+    if (CHUNK && REV && c0 >= 0 && !ckw[2]) {
+        // reverse pass in column chunks: every task leaves (its stop column, its best cell up to there); the task
+        // that finishes last walks them in scan order up to the first stop column (ssw.c:296,499)
+        const int cw = ckw[1];
+        if (lane == 0)
+            a.ck.task_res[task] = make_int4(termCol >= 0 ? termCol + cw : -1, candM, candM > 0 ? candCol + cw : -1, candRow);
+        int left = 0;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) left = atomicSub(a.ck.pair_left + pair, 1) - 1;
+        left = __shfl_sync(FULL, left, 0);
+        if (left > 0) return;
+        __threadfence();
+        if (lane == 0) {
+            const unsigned long long span = *reinterpret_cast<volatile unsigned long long*>(a.ck.pair_key + pair);
+            const int t0 = (int)(span >> 32), nt = (int)(span & 0xffffffffull);
+            candM = 0; candCol = -1; candRow = 0;
+            for (int t = t0; t < t0 + nt; ++t) {
+                const int4 r = __ldcg(a.ck.task_res + t);          // written by other SMs: read through L2
+                if (r.y > candM) { candM = r.y; candCol = r.z; candRow = r.w; }
+                if (r.x >= 0) break;
+            }
+        }
+        candM = __shfl_sync(FULL, candM, 0); candCol = __shfl_sync(FULL, candCol, 0); candRow = __shfl_sync(FULL, candRow, 0);
     }
 
     if (!REV) {
@@ -525,9 +566,9 @@ __global__ void __launch_bounds__(score_warps(K) * 32, 1) score_kernel(const Sco
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
         int pair, c0 = -1, c1 = 0;
-        if (CHUNK) { pair = a.ck.task_pair[idx]; c0 = a.ck.task_c0[idx]; c1 = a.ck.task_c1[idx]; }
+        if (CHUNK && a.ck.task_pair) { pair = a.ck.task_pair[idx]; c0 = a.ck.task_c0[idx]; c1 = a.ck.task_c1[idx]; }
         else pair = a.wl.idx[base + idx];
-        score_pair<K, TRUNC, REV, CHUNK>(a, pair, lut, rpw, ws, c0, c1);
+        score_pair<K, TRUNC, REV, CHUNK>(a, pair, lut, rpw, ws, c0, c1, idx);
         __syncwarp();
     }
 }
@@ -553,10 +594,12 @@ static cudaError_t launch_one(const ScoreArgs& a, int blocks, cudaStream_t st)
 template <int K>
 static cudaError_t launch_k(const ScoreArgs& a, bool trunc, bool rev, int blocks, cudaStream_t st)
 {
-    // chunk mode (ScoreArgs::ck) exists for the forward pass only and has its own instances, so that the
-    // common whole-pair kernels carry none of its code
-    if (!rev && a.ck.chunk_cols)
-        return trunc ? launch_one<K, true, false, true>(a, blocks, st) : launch_one<K, false, false, true>(a, blocks, st);
+    // chunk mode (ScoreArgs::ck, long references) has its own instances, so that the common whole-pair
+    // kernels carry none of its code
+    if (a.ck.chunk_cols) {
+        if (trunc) return rev ? launch_one<K, true, true, true>(a, blocks, st) : launch_one<K, true, false, true>(a, blocks, st);
+        return rev ? launch_one<K, false, true, true>(a, blocks, st) : launch_one<K, false, false, true>(a, blocks, st);
+    }
     if (trunc) return rev ? launch_one<K, true, true, false>(a, blocks, st) : launch_one<K, true, false, false>(a, blocks, st);
     return rev ? launch_one<K, false, true, false>(a, blocks, st) : launch_one<K, false, false, false>(a, blocks, st);
 }

@@ -321,11 +321,14 @@ def test_batched_collapse_call_sites(sw, oracle):
 
 def test_long_references_in_column_chunks(sw, oracle):
     """find_bsj window shape (find_bsj.py:182-233): short queries against references of tens to hundreds of
-    kilobases.  The forward pass runs as column-chunk tasks (ChunkPlan); every field incl. the second-best
-    score (which reads the merged column records) and the CIGAR must come out as for whole pairs"""
+    kilobases.  The forward pass runs as column-chunk tasks (ChunkPlan), the reverse pass as a bounded first
+    look plus chunk tasks for the pairs without a stop column; every field incl. the second-best score
+    (which reads the merged column records) and the CIGAR must come out as for whole pairs"""
     from ciri_long_b200 import workloads as W
     rng = np.random.default_rng(123)
-    for params in ((1, 1, 1, 1), (10, 4, 8, 2)):
+    # (3,2,2,2) / (2,1,1,1): gap_open == gap_extend with match != mismatch, where the reverse pass can jump over
+    # score1 without meeting it and then scans (here: in column-chunk tasks) the whole prefix
+    for params in ((1, 1, 1, 1), (10, 4, 8, 2), (3, 2, 2, 2), (2, 1, 1, 1)):
         qs, rs = [], []
         for k in range(14):
             n = int(rng.integers(33000, 140000))
