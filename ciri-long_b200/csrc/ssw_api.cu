@@ -130,7 +130,7 @@ struct ssw_batch {
 };
 
 
-// Which scoring schemes the device recurrences reproduce bit-exactly (see ssw_score.cu header):
+// Which scoring schemes the device recurrences reproduce bit-exactly (see ssw_score_impl.cuh header):
 // 5x5 matrix with a zero N row/column (the only matrix ssw_wrap.py:146-159 builds), gap_open >=
 // gap_extend >= 1 and 2*gap_extend >= the largest mismatch penalty (an insertion next to a deletion is
 // then never better than substitutions, which makes the reference's lazy-F bookkeeping unobservable).

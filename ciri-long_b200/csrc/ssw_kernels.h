@@ -4,7 +4,7 @@
 
 namespace sswb {
 
-// ---- score passes (ssw_score.cu)
+// ---- score passes (ssw_score_impl.cuh, instances in ssw_score_[a-d].cu)
 // ---- long references: the forward pass over column chunks
 // A zero-started pass over columns [c0 - ov, c1) gives the exact H values of columns [c0, c1) when
 // ov > m * (1 + maxMatch / gap_extend): a path that starts before the overlap has crossed more than ov
@@ -77,7 +77,7 @@ __host__ __device__ inline int first_pass_kind(int m, int go, int ge, int maxSco
     return (go == ge && 3LL * m * maxScore >= 4LL * (255 - bias)) ? 1 : 0;
 }
 
-// strip height (template parameter K of the score kernel) for a query of m rows; must match ssw_score.cu
+// strip height (template parameter K of the score kernel) for a query of m rows; must match ssw_score_impl.cuh
 __host__ __device__ inline int strip_height_for(int m, int trunc)
 {
     if (!trunc) return m <= VSTRIPS * KMAX ? (m + VSTRIPS - 1) / VSTRIPS : KMAX;

@@ -8,7 +8,7 @@
 namespace sswb {
 
 // rows per strip: GOTOH cuts the query into tiles of 64 equal strips; TRUNC gives each of the reference's
-// 8 segments (ceil(m/8) rows) its own G strips (ssw_score.cu)
+// 8 segments (ceil(m/8) rows) its own G strips (ssw_score_impl.cuh)
 __device__ __forceinline__ int strip_height(int m, int kind) { return strip_height_for(m, kind); }
 
 // which list a pair belongs to in `stage`; -1 = not part of this stage

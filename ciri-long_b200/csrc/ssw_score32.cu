@@ -1,6 +1,6 @@
 // ssw_score32.cu -- 32-bit score passes for the pairs the packed 16-bit kernels hand over.
 //
-// The packed kernels of ssw_score.cu keep scores in signed 16-bit halves and leave a pair alone as soon
+// The packed kernels of ssw_score_impl.cuh keep scores in signed 16-bit halves and leave a pair alone as soon
 // as its score comes near the range where the reference's own arithmetic starts to matter: the word
 // flavour saturates at 32767 (`_mm_adds_epi16`, ssw.c:442), and the truncated-F gate of the packed
 // kernel needs scores below 16000.  Such pairs (e.g. >3.3 kb near-perfect matches at match = 10) are
