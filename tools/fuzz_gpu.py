@@ -1,0 +1,90 @@
+"""Randomised parity sweep: the CUDA path against the UNMODIFIED reference library (oracle/_ref/libssw.so)
+on mixed shapes and random supported scoring schemes.  Test infrastructure (uses oracle/); prints one
+line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import multiprocessing as mp
+import numpy as np
+import ciri_long_b200
+from ciri_long_b200 import ssw_wrap as sw, workloads as W
+from oracle import oracle as O
+
+_ref = None
+def _init():
+    global _ref
+    _ref = O.RefLib()
+
+def _one(job):
+    q, r, mat, go, ge = job
+    e = _ref.align(q, r, mat, go, ge, flag=1)
+    if e is None:                                   # the reference gave up (its traceback left the band, ssw.c:716-733)
+        return None
+    return (tuple(e[k] for k in O.FIELDS), tuple(int(c) for c in e["cigar"]))
+
+def make_pairs(n, rng):
+    qs, rs = [], []
+    for k in range(n):
+        shape = rng.integers(0, 6)
+        if shape == 0:   m, nn = rng.integers(1, 80), rng.integers(1, 80)
+        elif shape == 1: m, nn = rng.integers(100, 900), rng.integers(300, 3000)
+        elif shape == 2: nn = rng.integers(50, 1200); m = max(1, nn + rng.integers(-30, 31))
+        elif shape == 3: m, nn = rng.integers(200, 2500), rng.integers(15, 80)
+        elif shape == 4: m, nn = rng.integers(900, 1300), rng.integers(1000, 1500)
+        else:            m, nn = rng.integers(20, 400), rng.integers(3000, 9000)
+        m, nn = int(m), int(nn)
+        r = rng.integers(0, 4, nn).astype(np.int8)
+        mode = rng.integers(0, 4)
+        if mode == 0 or nn < 4:
+            q = rng.integers(0, 4, m).astype(np.int8)
+        else:
+            L = min(m, nn); st = int(rng.integers(0, nn - L + 1))
+            rate = (0.02, 0.06, 0.15)[int(rng.integers(0, 3))]
+            q, _ = W.noisy_channel(r[st:st + L].copy(), np.array([L]), rng, sub=rate, ins=rate, dele=rate, max_run=int(rng.integers(1, 9)),
+                                   n_frac=(0.0, 0.02)[int(rng.integers(0, 2))])
+            if len(q) == 0: q = rng.integers(0, 4, 3).astype(np.int8)
+            if mode == 2:   # periodic reference: many equal-scoring placements (tie-breaking)
+                unit = r[:max(2, nn // int(rng.integers(2, 9)))]
+                r = np.tile(unit, nn // len(unit) + 1)[:nn].copy()
+        qs.append(q); rs.append(r)
+    return qs, rs
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+    schemes = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    fixed = [(1, 1, 1, 1), (10, 4, 8, 2), (2, 2, 3, 1), (3, 2, 2, 2), (2, 1, 1, 1), (5, 4, 6, 2)]
+    pool = mp.Pool(os.cpu_count(), initializer=_init)
+    total_bad = 0
+    for s in range(schemes):
+        if s < len(fixed): p = fixed[s]
+        else:
+            ge = int(rng.integers(1, 6)); go = ge + int(rng.integers(0, 8)); mis = int(rng.integers(1, 2 * ge + 1)); mat = int(rng.integers(1, 12))
+            p = (mat, mis, go, ge)
+        qs, rs = make_pairs(n, rng)
+        b = W.from_lists(qs, rs, p)
+        t0 = time.perf_counter()
+        with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, p[0], p[1], p[2], p[3], flag=1) as d:
+            d.run(); rec, cig = d.fetch()
+        t1 = time.perf_counter()
+        mat = O.make_mat(p[0], p[1])
+        exp = pool.map(_one, [(qs[i], rs[i], mat, p[2], p[3]) for i in range(n)], chunksize=64)
+        t2 = time.perf_counter()
+        bad = []
+        for i in range(n):
+            r = rec[i]
+            if exp[i] is None:
+                if (r["status"] & 0xff) == 0: bad.append((i, "reference returned NULL, device did not", len(qs[i]), len(rs[i])))
+                continue
+            got = (int(r["score1"]), int(r["score2"]), int(r["ref_begin1"]), int(r["ref_end1"]), int(r["read_begin1"]), int(r["read_end1"]), int(r["ref_end2"]))
+            gc = tuple(int(c) for c in cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]])
+            ok = (r["status"] & 0xff) == 0 and got == exp[i][0] and gc == exp[i][1]
+            if not ok and not (exp[i][0][0] == 0):          # score 0: the reference reads ref[-1] (undefined), fields still compared above
+                bad.append((i, int(r["status"]), len(qs[i]), len(rs[i]), got, exp[i][0], gc == exp[i][1]))
+            elif not ok and got != exp[i][0]:
+                bad.append((i, int(r["status"]), len(qs[i]), len(rs[i]), got, exp[i][0], gc == exp[i][1]))
+        total_bad += len(bad)
+        print("scheme %s pairs %d cells %.2e gpu %.2fs ref(%d cores) %.1fs mismatches %d %s" % (p, n, b.cells, t1 - t0, os.cpu_count(), t2 - t1, len(bad), bad[:3]), flush=True)
+    print("TOTAL mismatches", total_bad)
+
+if __name__ == "__main__":
+    main()
