@@ -292,13 +292,16 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 // cells above score1 only count if they occur before that column.  Strips ahead of the
                 // stop column keep running here: values above score1 are kept out of the best-cell
                 // tracking and only their first column is remembered (checked after the pass).
-                // (the DPX result must be consumed: ptxas 12.9 mis-allocates the destination of a VIMNMX whose
-                //  value is dead and only the predicates are used)
+                // One packed op says whether any half is above the target; which half is then decided on the scalar
+                // values.  (Testing the halves of `ov` itself miscompiles with ptxas 12.9: it takes both conditions
+                // from the predicate outputs of the VIMNMX, one predicate register for two halves, and a lane whose
+                // other half is an unused strip keeps its over-the-target cell -- found by tools/fuzz_gpu.py on
+                // multi-tile queries.)
                 const unsigned ov = addmax_relu(mxv, mtermP, 0u);              // max(mxv - score1, 0) per half
                 if (ov) {
                     const int skipc = CHUNK ? ckw[0] : 0;               // (chunk mode: warm-up columns do not count)
-                    if (ov & 0xffffu) { if (!CHUNK || cLo >= skipc) overCol = cLo < overCol ? cLo : overCol; mxv &= 0xffff0000u; }
-                    if (ov >> 16) { if (!CHUNK || cHi >= skipc) overCol = cHi < overCol ? cHi : overCol; mxv &= 0x0000ffffu; }
+                    if (lo16(mxv) - go > terminate) { if (!CHUNK || cLo >= skipc) overCol = cLo < overCol ? cLo : overCol; mxv &= 0xffff0000u; }
+                    if (hi16(mxv) - go > terminate) { if (!CHUNK || cHi >= skipc) overCol = cHi < overCol ? cHi : overCol; mxv &= 0x0000ffffu; }
                 }
             }
             bool pHi, pLo;
@@ -344,7 +347,9 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         auto refresh = [&]() {
             const int lo = lo16(best), hi = hi16(best);
             const int g = __reduce_max_sync(FULL, lo > hi ? lo : hi);
-            bestT = max_relu(bestT, pack2(g, g));
+            // g - 1: a cell that only equals the warp-wide maximum still counts if its column is earlier (ties go to
+            // the first column, ssw.c:286-292), and a strip that is ahead in time can be behind in columns
+            bestT = max_relu(bestT, pack2(g - 1, g - 1));
         };
         auto sweep = [&](auto multi) {
             int s0 = 0;

@@ -130,6 +130,26 @@ def fuzz_cases(rng):
     cases.append(dict(name="G6_n_and_unknown", params=(1, 1, 1, 1), ref="ACGTNNNNACGTACGTXX", query="ACGTACGTACGTACGTRY"))
     cases.append(dict(name="G7_leading_deletion", params=(10, 4, 8, 2), ref="GTGATTGCGTTTCTA", query="GGATATGACGACTA"))
     cases.append(dict(name="lowercase", params=(2, 2, 3, 1), ref="acgtacgtacgtTTGACCA", query="cgtacgtTTGAC"))
+    # found by tools/fuzz_gpu.py (round 1): queries of more than 1024 rows (several strip tiles) whose reverse pass
+    # meets score1 while strips ahead of the stop column already hold larger values ...
+    for p in ((1, 1, 1, 1), (2, 1, 1, 1), (3, 2, 2, 2)):
+        for t in range(10):
+            n = int(rng.integers(1000, 1500)); m = int(rng.integers(1050, 1400))
+            r = rng.integers(0, 4, size=n).astype(np.int8)
+            L = min(m, n); st = int(rng.integers(0, n - L + 1))
+            q = channel(r[st:st + L], .05, .05, .05, 4, rng)
+            cases.append(dict(name="multitile_%d_%d_%d_%d_%02d" % (p + (t,)), params=p, ref=to_str(r), query=to_str(q)))
+    # ... and periodic references, where several cells share the maximum and the first column must win even
+    # though a later column is computed earlier (different query rows)
+    for p in ((5, 5, 10, 3), (10, 4, 8, 2), (1, 1, 1, 1)):
+        for t in range(10):
+            n = int(rng.integers(300, 1400)); unit = rng.integers(0, 4, size=int(rng.integers(20, 200))).astype(np.int8)
+            r = np.tile(unit, n // len(unit) + 1)[:n].astype(np.int8)
+            m = int(rng.integers(100, 900)); L = min(m, n); st = int(rng.integers(0, n - L + 1))
+            q = channel(r[st:st + L], .03, .03, .03, 3, rng)
+            if len(q) < 2:
+                continue
+            cases.append(dict(name="periodic_%d_%d_%d_%d_%02d" % (p + (t,)), params=p, ref=to_str(r), query=to_str(q)))
     return cases
 
 

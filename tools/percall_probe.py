@@ -22,3 +22,18 @@ t0 = time.perf_counter()
 for i in range(len(j)):
     r = sw.Aligner(refs[i], 10, 4, 8, 2).align(qs[i])
 print("per-call tiny pair (50 x 20): %.3f ms/call" % ((time.perf_counter() - t0) / len(j) * 1e3))
+# the find_bsj shape through the drop-in: one clipped read end against a +-200 kb window (find_bsj.py:204-215)
+rng = np.random.default_rng(9)
+win = rng.integers(0, 4, 400000).astype(np.int8)
+ref = "".join(bases[win])
+al = sw.Aligner(ref, 1, 1, 1, 1)
+qs = []
+for k in range(8):
+    m = int(rng.integers(40, 400)); st = int(rng.integers(0, 400000 - m))
+    q, _ = W.noisy_channel(win[st:st + m].copy(), np.array([m]), rng)
+    qs.append("".join(bases[q]))
+al.align(qs[0])
+t0 = time.perf_counter()
+for q in qs:
+    r = al.align(q)
+print("per-call 40-400 nt vs 400 kb window: %.2f ms/call" % ((time.perf_counter() - t0) / len(qs) * 1e3))
