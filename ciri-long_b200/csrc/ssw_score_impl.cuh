@@ -358,6 +358,12 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 int s1 = s0 + RP_CHUNK < steps ? s0 + RP_CHUNK : steps;
                 if (s0 < sA) { if (s1 > sA) s1 = sA; }
                 else if (s0 < sB) { if (s1 > sB) s1 = sB; }
+                if (CHUNK && !REV) {
+                    // a block must not straddle the step at which the writer strip leaves the warm-up columns (it does
+                    // when the chunk's own part is shorter than the pipeline: the last chunk of a reference)
+                    const int sw = ckw[0] ? ckw[0] + wv : 0;
+                    if (s0 < sw && s1 > sw) s1 = sw;
+                }
                 const bool steady = s0 >= sA && s1 <= sB;
                 if (CHUNK && !REV) {
                     // column records of the chunk's own columns go to the pair's array, warm-up columns to scratch

@@ -345,6 +345,14 @@ def test_long_references_in_column_chunks(sw, oracle):
                 q, _ = W.noisy_channel(r[st:st + m].copy(), np.array([m]), rng)
             qs.append(q); rs.append(r)
         qs.append(rng.integers(0, 4, 200).astype(np.int8)); rs.append(rng.integers(0, 4, 70000).astype(np.int8))   # unrelated
+        # last chunk shorter than the 64-strip pipeline (chunks of 8192 columns in a batch this small): its columns
+        # must still reach the merged column records that the second-best scan reads
+        for tail in (1, 15, 63, 64, 100):
+            n = 8192 * 5 + tail
+            r = rng.integers(0, 4, n).astype(np.int8)
+            q, _ = W.noisy_channel(r[5000:5300].copy(), np.array([300]), rng)
+            r[n - len(q) - 3:n - 3] = q                               # a perfect copy that ends in the last chunk
+            qs.append(q); rs.append(r)
         b = W.from_lists(qs, rs, params, name="long-ref %s" % (params,))
         check_batch(sw, oracle, b)
 

@@ -1,6 +1,6 @@
 """Randomised parity sweep: the CUDA path against the UNMODIFIED reference library (oracle/_ref/libssw.so)
 on mixed shapes and random supported scoring schemes.  Test infrastructure (uses oracle/); prints one
-line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed."""
+line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed, family (mixed | edge | long)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiprocessing as mp
@@ -21,7 +21,43 @@ def _one(job):
         return None
     return (tuple(e[k] for k in O.FIELDS), tuple(int(c) for c in e["cigar"]))
 
-def make_pairs(n, rng):
+def make_edge_pairs(n, rng):
+    """degenerate inputs: one to three bases, homopolymers, all-N, identical sequences, query longer than reference"""
+    qs, rs = [], []
+    for k in range(n):
+        kind = rng.integers(0, 7)
+        if kind == 0:   q = rng.integers(0, 5, int(rng.integers(1, 4))); r = rng.integers(0, 5, int(rng.integers(1, 4)))
+        elif kind == 1: b = int(rng.integers(0, 4)); q = np.full(int(rng.integers(1, 300)), b); r = np.full(int(rng.integers(1, 600)), b)
+        elif kind == 2: q = np.full(int(rng.integers(1, 100)), 4); r = rng.integers(0, 5, int(rng.integers(1, 200)))
+        elif kind == 3: q = rng.integers(0, 4, int(rng.integers(1, 1500))); r = q.copy()
+        elif kind == 4: q = rng.integers(0, 4, int(rng.integers(200, 2000))); r = q[int(rng.integers(0, 100)):][:int(rng.integers(5, 60))].copy()
+        elif kind == 5: r = rng.integers(0, 4, int(rng.integers(16, 40))); q = np.concatenate([r] * int(rng.integers(2, 30)))
+        else:           q = rng.integers(0, 2, int(rng.integers(1, 500))); r = rng.integers(0, 2, int(rng.integers(1, 900)))      # two-letter alphabet: many ties
+        if len(r) == 0: r = np.array([0])
+        qs.append(q.astype(np.int8)); rs.append(r.astype(np.int8))
+    return qs, rs
+
+
+def make_long_pairs(n, rng):
+    """references beyond 32 k columns (column-chunk tasks), queries from 20 bases to more than one tile"""
+    qs, rs = [], []
+    genome = rng.integers(0, 4, 400000).astype(np.int8)
+    for k in range(n):
+        nn = int(rng.integers(33000, 120000)); a = int(rng.integers(0, len(genome) - nn))
+        r = genome[a:a + nn].copy()
+        m = int(rng.choice([20, 50, 120, 250, 340, 400, 500, 800, 1100, 1500]))
+        st = int(rng.integers(0, nn - m))
+        rate = (0.02, 0.06, 0.12)[int(rng.integers(0, 3))]
+        q, _ = W.noisy_channel(r[st:st + m].copy(), np.array([m]), rng, sub=rate, ins=rate, dele=rate, n_frac=0.01)
+        if rng.random() < 0.3:      # a second copy of the query elsewhere: second-best score over merged column records
+            st2 = int(rng.integers(0, nn - len(q))); r[st2:st2 + len(q)] = q
+        qs.append(q); rs.append(r)
+    return qs, rs
+
+
+def make_pairs(n, rng, family="mixed"):
+    if family == "edge": return make_edge_pairs(n, rng)
+    if family == "long": return make_long_pairs(n, rng)
     qs, rs = [], []
     for k in range(n):
         shape = rng.integers(0, 6)
@@ -52,6 +88,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
     schemes = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    family = sys.argv[4] if len(sys.argv) > 4 else "mixed"
     fixed = [(1, 1, 1, 1), (10, 4, 8, 2), (2, 2, 3, 1), (3, 2, 2, 2), (2, 1, 1, 1), (5, 4, 6, 2)]
     pool = mp.Pool(os.cpu_count(), initializer=_init)
     total_bad = 0
@@ -60,7 +97,7 @@ def main():
         else:
             ge = int(rng.integers(1, 6)); go = ge + int(rng.integers(0, 8)); mis = int(rng.integers(1, 2 * ge + 1)); mat = int(rng.integers(1, 12))
             p = (mat, mis, go, ge)
-        qs, rs = make_pairs(n, rng)
+        qs, rs = make_pairs(n, rng, family)
         b = W.from_lists(qs, rs, p)
         t0 = time.perf_counter()
         with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, p[0], p[1], p[2], p[3], flag=1) as d:
