@@ -1,6 +1,6 @@
 """Randomised parity sweep: the CUDA path against the UNMODIFIED reference library (oracle/_ref/libssw.so)
 on mixed shapes and random supported scoring schemes.  Test infrastructure (uses oracle/); prints one
-line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed, family (mixed | edge | long)."""
+line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed, family (mixed | edge | long), "flags" to vary flag and mask length."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiprocessing as mp
@@ -15,8 +15,8 @@ def _init():
     _ref = O.RefLib()
 
 def _one(job):
-    q, r, mat, go, ge = job
-    e = _ref.align(q, r, mat, go, ge, flag=1)
+    q, r, mat, go, ge, flag, mask = job
+    e = _ref.align(q, r, mat, go, ge, flag=flag, mask_len=mask)
     if e is None:                                   # the reference gave up (its traceback left the band, ssw.c:716-733)
         return None
     return (tuple(e[k] for k in O.FIELDS), tuple(int(c) for c in e["cigar"]))
@@ -89,6 +89,7 @@ def main():
     schemes = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
     family = sys.argv[4] if len(sys.argv) > 4 else "mixed"
+    vary = len(sys.argv) > 5 and sys.argv[5] == "flags"
     fixed = [(1, 1, 1, 1), (10, 4, 8, 2), (2, 2, 3, 1), (3, 2, 2, 2), (2, 1, 1, 1), (5, 4, 6, 2)]
     pool = mp.Pool(os.cpu_count(), initializer=_init)
     total_bad = 0
@@ -99,12 +100,18 @@ def main():
             p = (mat, mis, go, ge)
         qs, rs = make_pairs(n, rng, family)
         b = W.from_lists(qs, rs, p)
+        # the ssw_align flag (ssw.c:779-869) and the mask length of the second-best search, when asked for
+        flag = int(rng.choice([0, 1, 2, 4])) if vary else 1
+        masks = None
+        if vary:
+            masks = np.array([O.default_mask_len(len(q)) if u < 0.4 else (15 if u < 0.6 else (int(rng.integers(1, 15)) if u < 0.8 else int(rng.integers(16, 2000))))
+                              for q, u in zip(qs, rng.random(n))], dtype=np.int32)
         t0 = time.perf_counter()
-        with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, p[0], p[1], p[2], p[3], flag=1) as d:
+        with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, p[0], p[1], p[2], p[3], flag=flag, mask_len=masks) as d:
             d.run(); rec, cig = d.fetch()
         t1 = time.perf_counter()
         mat = O.make_mat(p[0], p[1])
-        exp = pool.map(_one, [(qs[i], rs[i], mat, p[2], p[3]) for i in range(n)], chunksize=64)
+        exp = pool.map(_one, [(qs[i], rs[i], mat, p[2], p[3], flag, None if masks is None else int(masks[i])) for i in range(n)], chunksize=64)
         t2 = time.perf_counter()
         bad = []
         for i in range(n):
@@ -120,7 +127,7 @@ def main():
             elif not ok and got != exp[i][0]:
                 bad.append((i, int(r["status"]), len(qs[i]), len(rs[i]), got, exp[i][0], gc == exp[i][1]))
         total_bad += len(bad)
-        print("scheme %s pairs %d cells %.2e gpu %.2fs ref(%d cores) %.1fs mismatches %d %s" % (p, n, b.cells, t1 - t0, os.cpu_count(), t2 - t1, len(bad), bad[:3]), flush=True)
+        print("scheme %s flag %d pairs %d cells %.2e gpu %.2fs ref(%d cores) %.1fs mismatches %d %s" % (p, flag, n, b.cells, t1 - t0, os.cpu_count(), t2 - t1, len(bad), bad[:3]), flush=True)
     print("TOTAL mismatches", total_bad)
 
 if __name__ == "__main__":
