@@ -113,7 +113,7 @@ def main():
         mat = O.make_mat(p[0], p[1])
         exp = pool.map(_one, [(qs[i], rs[i], mat, p[2], p[3], flag, None if masks is None else int(masks[i])) for i in range(n)], chunksize=64)
         t2 = time.perf_counter()
-        bad = []
+        bad = []; ub = 0
         for i in range(n):
             r = rec[i]
             if exp[i] is None:
@@ -121,13 +121,18 @@ def main():
                 continue
             got = (int(r["score1"]), int(r["score2"]), int(r["ref_begin1"]), int(r["ref_end1"]), int(r["read_begin1"]), int(r["read_end1"]), int(r["ref_end2"]))
             gc = tuple(int(c) for c in cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]])
+            if (r["status"] & 0xff) == 1 and got == exp[i][0]:
+                # the traceback leaves the band: the reference goes on reading direction bytes it never wrote
+                # (ssw.c:643-644 with j < beg) and returns whatever that memory yields; the device reports the pair
+                ub += 1
+                continue
             ok = (r["status"] & 0xff) == 0 and got == exp[i][0] and gc == exp[i][1]
             if not ok and not (exp[i][0][0] == 0):          # score 0: the reference reads ref[-1] (undefined), fields still compared above
                 bad.append((i, int(r["status"]), len(qs[i]), len(rs[i]), got, exp[i][0], gc == exp[i][1]))
             elif not ok and got != exp[i][0]:
                 bad.append((i, int(r["status"]), len(qs[i]), len(rs[i]), got, exp[i][0], gc == exp[i][1]))
         total_bad += len(bad)
-        print("scheme %s flag %d pairs %d cells %.2e gpu %.2fs ref(%d cores) %.1fs mismatches %d %s" % (p, flag, n, b.cells, t1 - t0, os.cpu_count(), t2 - t1, len(bad), bad[:3]), flush=True)
+        print("scheme %s flag %d pairs %d cells %.2e gpu %.2fs ref(%d cores) %.1fs mismatches %d traceback-left-band %d %s" % (p, flag, n, b.cells, t1 - t0, os.cpu_count(), t2 - t1, len(bad), ub, bad[:3]), flush=True)
     print("TOTAL mismatches", total_bad)
 
 if __name__ == "__main__":
