@@ -1,6 +1,6 @@
 """Randomised parity sweep: the CUDA path against the UNMODIFIED reference library (oracle/_ref/libssw.so)
 on mixed shapes and random supported scoring schemes.  Test infrastructure (uses oracle/); prints one
-line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed, family (mixed | edge | long), "flags" to vary flag and mask length."""
+line per scheme and the first mismatches.  argv: pairs per scheme, number of schemes, seed, family (mixed | edge | long | both | big), "flags" to vary flag and mask length."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiprocessing as mp
@@ -58,6 +58,20 @@ def make_long_pairs(n, rng):
 def make_pairs(n, rng, family="mixed"):
     if family == "edge": return make_edge_pairs(n, rng)
     if family == "long": return make_long_pairs(n, rng)
+    if family == "big":                                     # scores around and beyond the 16-bit range (32-bit kernels, saturation)
+        qs, rs = [], []
+        for k in range(n):
+            nn = int(rng.integers(2500, 4800)); r = rng.integers(0, 4, nn).astype(np.int8)
+            m = int(rng.integers(2500, nn + 1)); st = int(rng.integers(0, nn - m + 1))
+            rate = (0.0, 0.005, 0.02, 0.05)[int(rng.integers(0, 4))]
+            q, _ = W.noisy_channel(r[st:st + m].copy(), np.array([m]), rng, sub=rate, ins=rate, dele=rate)
+            qs.append(q); rs.append(r)
+        return qs, rs
+    if family == "both":                                    # short and long references in one batch, shuffled
+        qa, ra = make_pairs(n - n // 10, rng, "mixed"); qb, rb = make_long_pairs(n // 10, rng)
+        order = rng.permutation(n)
+        qs, rs = qa + qb, ra + rb
+        return [qs[i] for i in order], [rs[i] for i in order]
     qs, rs = [], []
     for k in range(n):
         shape = rng.integers(0, 6)
