@@ -357,6 +357,55 @@ def test_long_references_in_column_chunks(sw, oracle):
         check_batch(sw, oracle, b)
 
 
+def test_randomized_mixture(sw, oracle):
+    """a small edition of tools/fuzz_gpu.py (which sweeps against the reference library itself): mixed shapes incl.
+    periodic references (equal-score ties), queries of more than one strip tile and degenerate inputs, three
+    scoring schemes per run, every field and CIGAR against the oracle"""
+    from ciri_long_b200 import workloads as W
+    rng = np.random.default_rng(2026)
+    for params in ((1, 1, 1, 1), (2, 1, 1, 1), (5, 5, 10, 3)):
+        qs, rs = [], []
+        for k in range(260):
+            shape = k % 7
+            if shape == 0:   m, n = int(rng.integers(1, 60)), int(rng.integers(1, 60))
+            elif shape == 1: m, n = int(rng.integers(100, 700)), int(rng.integers(300, 2500))
+            elif shape == 2: n = int(rng.integers(50, 900)); m = max(1, n + int(rng.integers(-30, 31)))
+            elif shape == 3: m, n = int(rng.integers(200, 1800)), int(rng.integers(15, 80))
+            elif shape == 4: m, n = int(rng.integers(1030, 1300)), int(rng.integers(1000, 1400))
+            elif shape == 5: m, n = int(rng.integers(20, 300)), int(rng.integers(2000, 6000))
+            else:            m, n = int(rng.integers(1, 400)), int(rng.integers(1, 700))
+            if shape == 6:
+                r = rng.integers(0, 2, n).astype(np.int8); q = rng.integers(0, 2, m).astype(np.int8)       # two letters: ties everywhere
+            else:
+                r = rng.integers(0, 4, n).astype(np.int8)
+                if k % 3 == 2:                                       # periodic reference
+                    unit = r[:max(2, n // int(rng.integers(2, 9)))]
+                    r = np.tile(unit, n // len(unit) + 1)[:n].copy()
+                L = min(m, n); st = int(rng.integers(0, n - L + 1))
+                rate = (0.02, 0.06, 0.15)[k % 3]
+                q, _ = W.noisy_channel(r[st:st + L].copy(), np.array([L]), rng, sub=rate, ins=rate, dele=rate, n_frac=0.01 * (k % 2))
+                if len(q) == 0:
+                    q = rng.integers(0, 4, 3).astype(np.int8)
+            qs.append(q); rs.append(r)
+        b = W.from_lists(qs, rs, params, name="randomized %s" % (params,))
+        rec, cig = run_batch(sw, b)
+        mat = O.make_mat(params[0], params[1])
+        bad = []
+        for i in range(len(b)):
+            exp = oracle.align(b.query(i), b.ref(i), mat, params[2], params[3], flag=1)
+            r = rec[i]
+            if exp is None:                                          # traceback left the band: both sides must say so
+                if (r["status"] & 0xff) == 0:
+                    bad.append((i, "oracle: traceback error, device: ok"))
+                continue
+            got = dict(score=int(r["score1"]), score2=int(r["score2"]), ref_begin=int(r["ref_begin1"]), ref_end=int(r["ref_end1"]),
+                       read_begin=int(r["read_begin1"]), read_end=int(r["read_end1"]), ref_end2=int(r["ref_end2"]),
+                       cigar=cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]].tolist())
+            if (r["status"] & 0xff) != 0 or not O.same(got, exp):
+                bad.append((i, int(r["status"]), len(qs[i]), len(rs[i]), {k: got[k] for k in O.FIELDS}, {k: exp[k] for k in O.FIELDS}))
+        assert not bad, "%s: %d mismatches, first: %s" % (b.name, len(bad), bad[:3])
+
+
 def test_mixed_length_batch(sw, oracle):
     """C5-style mixture under one scoring scheme: tiny junction pairs, read-vs-read segments, long reads vs
     50-nt junctions, shuffled into one batch (every kernel instance and list class at once)"""
