@@ -77,6 +77,7 @@ struct ssw_batch {
     // d_seqs - seq_lo so the caller's offsets are used unchanged)
     long long seq_lo = 0, seq_hi = 0;
     std::vector<int32_t> h_mask;
+    bool ascii_done = false;
     std::vector<int64_t> h_col_off;
     int8_t* d_seqs = nullptr;
     long long *d_qoff = nullptr, *d_roff = nullptr;
@@ -381,6 +382,16 @@ static int enqueue_cigar_stage(ssw_batch* b, int* launches)
     CU_TRY(launch_band(2, ba, b->wblocks, st));
     *launches += 1;
     *launches += 2;
+    return SSW_OK;
+}
+
+extern "C" int ssw_batch_encode_ascii(ssw_batch* b)
+{
+    if (!b) return SSW_ERR_ARG;
+    if (b->ascii_done) return SSW_OK;
+    CU_TRY(cudaSetDevice(b->device));
+    CU_TRY(encode_ascii(b->d_seqs, b->seq_hi - b->seq_lo, b->stream));
+    b->ascii_done = true;
     return SSW_OK;
 }
 

@@ -109,6 +109,9 @@ cudaError_t expand_tasks(const WorkList& wl, int max_pairs, bool rev, const Batc
                          int32_t* task_count, cudaStream_t st, int* launches);
 cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet& ls, cudaStream_t st, int* launches);
 
+// ASCII letters -> codes 0..4, in place (ssw_wrap.py:234-252 on the device)
+cudaError_t encode_ascii(int8_t* seqs, long long n, cudaStream_t st);
+
 // clear status bits (and the CIGAR window) of every pair, e.g. before the CIGAR pass is repeated
 cudaError_t clear_status_bits(const BatchView& b, int bits, cudaStream_t st);
 

@@ -170,6 +170,47 @@ cudaError_t expand_tasks(const WorkList& wl, int max_pairs, bool rev, const Batc
     return cudaGetLastError();
 }
 
+// ---- ASCII -> {0..4} on the device: the host uploads the raw letters and this
+// pass replaces the per-base encode of ssw_wrap.py:234-252 (A C G T N in either case, anything else N)
+__global__ void encode_ascii_kernel(int8_t* seqs, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x * 16;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n; i += stride) {
+        // 16 bytes per thread and step when the tail allows it
+        if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(seqs + i) & 15) == 0)) {
+            uint4 v = *reinterpret_cast<uint4*>(seqs + i);
+            unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned c = ((w[k] >> (8 * b)) & 0xffu) | 0x20u;         // lower case
+                    const unsigned code = c == 'a' ? 0u : c == 'c' ? 1u : c == 'g' ? 2u : c == 't' ? 3u : 4u;
+                    o |= code << (8 * b);
+                }
+                w[k] = o;
+            }
+            *reinterpret_cast<uint4*>(seqs + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (long long j = i; j < n && j < i + 16; ++j) {
+                const unsigned c = (unsigned)(unsigned char)seqs[j] | 0x20u;
+                seqs[j] = (int8_t)(c == 'a' ? 0 : c == 'c' ? 1 : c == 'g' ? 2 : c == 't' ? 3 : 4);
+            }
+        }
+    }
+}
+
+cudaError_t encode_ascii(int8_t* seqs, long long n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n / 16 + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < 1) blocks = 1;
+    encode_ascii_kernel<<<(int)blocks, 256, 0, st>>>(seqs, n);
+    return cudaGetLastError();
+}
+
 __global__ void clear_status_kernel(BatchView b, int bits)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -33,6 +33,9 @@ for _i, _b in enumerate("ACGTN"):
     _ENC[ord(_b.lower())] = _i
 
 
+_ENC_TABLE = bytes(int(v) for v in _ENC)
+
+
 def encode_dna(seq):
     """ASCII -> {0..4} (A C G T N, either case, anything else 4): ssw_wrap.py:234-252 without the
     per-base Python loop."""
@@ -40,7 +43,7 @@ def encode_dna(seq):
         return np.ascontiguousarray(seq, dtype=np.int8)
     if isinstance(seq, str):
         seq = seq.encode("latin-1", "replace")
-    return _ENC[np.frombuffer(seq, dtype=np.uint8)]
+    return np.frombuffer(bytes(seq).translate(_ENC_TABLE), dtype=np.int8)
 
 
 class CAlignRes(Structure):
@@ -92,6 +95,8 @@ def _load():
                                      c_void_p, c_void_p, POINTER(SSWScoring)]
     lib.ssw_batch_run.restype = c_int
     lib.ssw_batch_run.argtypes = [c_void_p]
+    lib.ssw_batch_encode_ascii.restype = c_int
+    lib.ssw_batch_encode_ascii.argtypes = [c_void_p]
     lib.ssw_batch_fetch.restype = c_int
     lib.ssw_batch_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64)]
     lib.ssw_batch_launch_count.restype = c_int64
@@ -136,7 +141,7 @@ class DeviceBatch(object):
     libssw = _load()
 
     def __init__(self, seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend,
-                 flag=1, mask_len=None, device=0, stream=None, filters=0, filterd=0):
+                 flag=1, mask_len=None, device=0, stream=None, filters=0, filterd=0, ascii=False):
         self.seqs = np.ascontiguousarray(seqs, dtype=np.int8)
         self.q_off = np.ascontiguousarray(q_off, dtype=np.int64)
         self.q_len = np.ascontiguousarray(q_len, dtype=np.int32)
@@ -152,6 +157,11 @@ class DeviceBatch(object):
             None if self.mask_len is None else self.mask_len.ctypes.data, byref(self.scoring))
         if not self.handle:
             raise SSWCudaError(self.libssw.ssw_cuda_last_error().decode())
+        if ascii:
+            # `seqs` holds the raw letters: the encode of ssw_wrap.py:234-252 runs on the device
+            rc = self.libssw.ssw_batch_encode_ascii(self.handle)
+            if rc != 0:
+                raise SSWCudaError("ssw_batch_encode_ascii: %d %s" % (rc, self.libssw.ssw_cuda_last_error().decode()))
 
     @property
     def h2d_bytes(self):
@@ -398,27 +408,48 @@ class PyAlignRes(object):
 
 
 #~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~#
-def pack_pairs(refs, queries, shared_ref=False):
-    """Concatenate encoded sequences into the struct-of-arrays layout of ssw_batch_create."""
-    q = [encode_dna(x) for x in queries]
-    if shared_ref:
-        r0 = encode_dna(refs[0]) if len(refs) else np.zeros(0, np.int8)
-        r = [r0]
+def _encode_many(seqs):
+    """Encode a list of sequences with ONE LUT pass over their concatenation; returns (codes, lengths)."""
+    if all(isinstance(x, str) for x in seqs):
+        lens = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
+        blob = "".join(seqs).encode("latin-1", "replace").translate(_ENC_TABLE)     # C-speed table lookup
+        return np.frombuffer(blob, dtype=np.int8), lens
+    parts = [encode_dna(x) for x in seqs]
+    lens = np.fromiter(map(len, parts), dtype=np.int64, count=len(parts))
+    return (np.concatenate(parts) if parts else np.zeros(0, np.int8)), lens
+
+
+def pack_pairs(refs, queries, shared_ref=False, raw=False):
+    """Concatenate the sequences into the struct-of-arrays layout of ssw_batch_create (references first, then
+    queries; with ``shared_ref`` the one reference is stored once).  Returns (seqs, q_off, q_len, r_off, r_len);
+    with ``raw=True`` a sixth item says whether ``seqs`` still holds ASCII letters (all inputs were ``str``: one
+    join, no host-side table pass -- the device encodes them, DeviceBatch(ascii=True))."""
+    refs = list(refs[:1]) if shared_ref else list(refs)
+    queries = list(queries)
+    is_ascii = False
+    if all(isinstance(x, str) for x in refs) and all(isinstance(x, str) for x in queries):
+        r_lens = np.fromiter(map(len, refs), dtype=np.int64, count=len(refs))
+        q_lens = np.fromiter(map(len, queries), dtype=np.int64, count=len(queries))
+        blob = "".join(refs + queries).encode("latin-1", "replace")
+        if raw:
+            is_ascii = True
+        else:
+            blob = blob.translate(_ENC_TABLE)
+        seqs = np.frombuffer(blob, dtype=np.int8)
     else:
-        r = [encode_dna(x) for x in refs]
-    q_len = np.array([len(x) for x in q], dtype=np.int32)
-    lens = [len(x) for x in r] + [int(x) for x in q_len]
-    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    seqs = np.concatenate(r + q) if (r or q) else np.zeros(0, np.int8)
-    nr = len(r)
+        r_codes, r_lens = _encode_many(refs)
+        q_codes, q_lens = _encode_many(queries)
+        seqs = np.concatenate([r_codes, q_codes]) if (len(r_codes) or len(q_codes)) else np.zeros(0, np.int8)
+    nq = len(q_lens)
     if shared_ref:
-        r_off = np.zeros(len(q), dtype=np.int64)
-        r_len = np.full(len(q), len(r[0]), dtype=np.int32)
+        r_off = np.zeros(nq, dtype=np.int64)
+        r_len = np.full(nq, int(r_lens[0]) if len(r_lens) else 0, dtype=np.int32)
     else:
-        r_off = offs[:nr].copy()
-        r_len = np.array([len(x) for x in r], dtype=np.int32)
-    q_off = offs[nr:nr + len(q)].copy()
-    return np.ascontiguousarray(seqs, dtype=np.int8), q_off, q_len, r_off, r_len
+        r_off = (np.cumsum(r_lens) - r_lens).astype(np.int64)
+        r_len = r_lens.astype(np.int32)
+    q_off = (int(r_lens.sum()) + np.cumsum(q_lens) - q_lens).astype(np.int64)
+    out = (np.ascontiguousarray(seqs, dtype=np.int8), q_off, q_lens.astype(np.int32), r_off, r_len)
+    return out + (is_ascii,) if raw else out
 
 
 def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, report_secondary=False,
@@ -431,14 +462,19 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
         raise ValueError("refs and queries differ in length")
     if not len(queries):
         return []
-    seqs, q_off, q_len, r_off, r_len = pack_pairs(refs, queries, _shared_ref)
+    # SSW_CUDA_DEVICE_ENCODE=1: upload the raw letters and let the device encode them (ssw_batch_encode_ascii)
+    if os.environ.get("SSW_CUDA_DEVICE_ENCODE") == "1":
+        seqs, q_off, q_len, r_off, r_len, is_ascii = pack_pairs(refs, queries, _shared_ref, raw=True)
+    else:
+        seqs, q_off, q_len, r_off, r_len = pack_pairs(refs, queries, _shared_ref)
+        is_ascii = False
     if need_cigar is None:
         need_cigar = report_cigar
     # flag 1 = begin + CIGAR (what the reference wrapper always asks for); flag 8 is not defined by the
     # reference -- the begin-only mode is expressed with the distance filter: bit 2 with filterd < 0
     flag = 1 if need_cigar else 4
     with DeviceBatch(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend, flag=flag,
-                     device=device, filterd=0 if need_cigar else -1) as b:
+                     device=device, filterd=0 if need_cigar else -1, ascii=is_ascii) as b:
         b.run()
         rec, cig = b.fetch()
     out = []

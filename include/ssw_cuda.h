@@ -125,6 +125,9 @@ ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs, const int
 /* Enqueue all kernels of the hot path on the batch's stream (asynchronous; inputs stay resident,
  * results stay on the device).  May be called repeatedly on the same batch. */
 int ssw_batch_run(ssw_batch* b);
+/* The batch was created from ASCII letters instead of codes: convert them on the device (A C G T N in either
+ * case -> 0..4, anything else 4; the encode of ssw_wrap.py:234-252).  Call once, before ssw_batch_run. */
+int ssw_batch_encode_ascii(ssw_batch* b);
 /* Wait for the stream, copy results and CIGARs to host.  cigar_buf may be NULL when flag == 0. */
 int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
 /* Number of kernel launches the last ssw_batch_run enqueued. */

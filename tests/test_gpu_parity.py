@@ -406,6 +406,39 @@ def test_randomized_mixture(sw, oracle):
         assert not bad, "%s: %d mismatches, first: %s" % (b.name, len(bad), bad[:3])
 
 
+@pytest.mark.parametrize("device_encode", ["0"])
+def test_string_batches(sw, monkeypatch, device_encode):
+    """align_pairs on str inputs: one join and one table pass on the host, or (SSW_CUDA_DEVICE_ENCODE=1) the raw
+    letters uploaded and converted on the device (ssw_wrap.py:234-252: A C G T N in either case, anything else
+    N); same results as on pre-encoded arrays"""
+    monkeypatch.setenv("SSW_CUDA_DEVICE_ENCODE", device_encode)
+    rng = np.random.default_rng(5)
+    letters = np.array(list("ACGTacgtNnXR-*"))
+    p = [0.2, 0.2, 0.2, 0.2, 0.03, 0.03, 0.03, 0.03, 0.02, 0.02, 0.01, 0.01, 0.01, 0.01]
+    refs, qs = [], []
+    for k in range(300):
+        n = int(rng.integers(1, 1500)); r = "".join(letters[rng.choice(len(letters), n, p=p)])
+        if k % 2:
+            st = int(rng.integers(0, n)); q = r[st:st + int(rng.integers(1, 400))].swapcase()
+        else:
+            q = "".join(letters[rng.choice(len(letters), int(rng.integers(1, 300)), p=p)])
+        refs.append(r); qs.append(q)
+    a = sw.align_pairs(refs, qs, 2, 2, 3, 1, report_secondary=True, report_cigar=True)
+    b = sw.align_pairs([sw.encode_dna(x) for x in refs], [sw.encode_dna(x) for x in qs], 2, 2, 3, 1, report_secondary=True, report_cigar=True)
+    for x, y in zip(a, b):
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert (x.score, x.score2, x.ref_begin, x.ref_end, x.query_begin, x.query_end, x.ref_end2, x.cigar_string) == \
+                   (y.score, y.score2, y.ref_begin, y.ref_end, y.query_begin, y.query_end, y.ref_end2, y.cigar_string)
+    # one reference, many queries (Aligner.align_batch)
+    al = sw.Aligner(refs[0], 2, 2, 3, 1, report_cigar=True)
+    got = al.align_batch(qs[:40])
+    for q, g in zip(qs[:40], got):
+        e = al.align(q)
+        assert (g.score, g.ref_begin, g.ref_end, g.query_begin, g.query_end, g.cigar_string) == \
+               (e.score, e.ref_begin, e.ref_end, e.query_begin, e.query_end, e.cigar_string)
+
+
 def test_mixed_length_batch(sw, oracle):
     """C5-style mixture under one scoring scheme: tiny junction pairs, read-vs-read segments, long reads vs
     50-nt junctions, shuffled into one batch (every kernel instance and list class at once)"""
