@@ -462,8 +462,9 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
         raise ValueError("refs and queries differ in length")
     if not len(queries):
         return []
-    # SSW_CUDA_DEVICE_ENCODE=1: upload the raw letters and let the device encode them (ssw_batch_encode_ascii)
-    if os.environ.get("SSW_CUDA_DEVICE_ENCODE") == "1":
+    # str inputs: upload the raw letters and let the device encode them (ssw_batch_encode_ascii);
+    # SSW_CUDA_DEVICE_ENCODE=0 keeps the table pass on the host
+    if os.environ.get("SSW_CUDA_DEVICE_ENCODE", "1") != "0":
         seqs, q_off, q_len, r_off, r_len, is_ascii = pack_pairs(refs, queries, _shared_ref, raw=True)
     else:
         seqs, q_off, q_len, r_off, r_len = pack_pairs(refs, queries, _shared_ref)

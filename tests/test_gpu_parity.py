@@ -406,7 +406,7 @@ def test_randomized_mixture(sw, oracle):
         assert not bad, "%s: %d mismatches, first: %s" % (b.name, len(bad), bad[:3])
 
 
-@pytest.mark.parametrize("device_encode", ["0"])
+@pytest.mark.parametrize("device_encode", ["0", "1"])
 def test_string_batches(sw, monkeypatch, device_encode):
     """align_pairs on str inputs: one join and one table pass on the host, or (SSW_CUDA_DEVICE_ENCODE=1) the raw
     letters uploaded and converted on the device (ssw_wrap.py:234-252: A C G T N in either case, anything else
