@@ -453,15 +453,19 @@ def pack_pairs(refs, queries, shared_ref=False, raw=False):
 
 
 def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, report_secondary=False,
-                report_cigar=False, min_score=0, min_len=0, device=0, need_cigar=None, _shared_ref=False):
+                report_cigar=False, min_score=0, min_len=0, device=0, need_cigar=None, _shared_ref=False,
+                as_records=False):
     """Batched equivalent of ``[Aligner(r, ...).align(q, min_score, min_len) for r, q in zip(refs, queries)]``.
 
     ``need_cigar`` defaults to ``report_cigar``: callers that never read ``cigar_string`` (every CIRI-long
-    site except collapse.py:373-387) may skip the CIGAR pass; begin coordinates are still computed."""
+    site except collapse.py:373-387) may skip the CIGAR pass; begin coordinates are still computed.
+    ``as_records=True`` returns ``(records, cigar_ops)`` -- the RESULT_DTYPE array of the C interface and the
+    uint32 op buffer its ``cigar_off`` / ``cigar_len`` index -- instead of one Python object per pair, which
+    is what bounds this call for large batches (min_score / min_len are then left to the caller)."""
     if len(refs) != len(queries):
         raise ValueError("refs and queries differ in length")
     if not len(queries):
-        return []
+        return (np.zeros(0, dtype=RESULT_DTYPE), np.zeros(0, dtype=np.uint32)) if as_records else []
     # str inputs: upload the raw letters and let the device encode them (ssw_batch_encode_ascii);
     # SSW_CUDA_DEVICE_ENCODE=0 keeps the table pass on the host
     if os.environ.get("SSW_CUDA_DEVICE_ENCODE", "1") != "0":
@@ -478,6 +482,8 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
                      device=device, filterd=0 if need_cigar else -1, ascii=is_ascii) as b:
         b.run()
         rec, cig = b.fetch()
+    if as_records:
+        return rec, cig
     out = []
     for i in range(len(queries)):
         r = rec[i]

@@ -430,6 +430,12 @@ def test_string_batches(sw, monkeypatch, device_encode):
         if x is not None:
             assert (x.score, x.score2, x.ref_begin, x.ref_end, x.query_begin, x.query_end, x.ref_end2, x.cigar_string) == \
                    (y.score, y.score2, y.ref_begin, y.ref_end, y.query_begin, y.query_end, y.ref_end2, y.cigar_string)
+    # the record form of the same call
+    rec, cig = sw.align_pairs(refs, qs, 2, 2, 3, 1, report_cigar=True, as_records=True)
+    for x, r in zip(a, rec):
+        if x is not None:
+            assert (x.score, x.ref_begin, x.ref_end, x.query_begin, x.query_end) == \
+                   (int(r["score1"]), int(r["ref_begin1"]), int(r["ref_end1"]), int(r["read_begin1"]), int(r["read_end1"]))
     # one reference, many queries (Aligner.align_batch)
     al = sw.Aligner(refs[0], 2, 2, 3, 1, report_cigar=True)
     got = al.align_batch(qs[:40])
