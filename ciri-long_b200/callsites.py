@@ -18,6 +18,17 @@ _COMP = str.maketrans("ATCGNatcgn", "TAGCNtagcn")
 Hit = namedtuple("Hit", "q_st q_en r_st r_en strand")
 
 
+def _coords(refs, queries, match, mismatch, gap_open, gap_extend, device, shared_ref=False):
+    """Score and coordinates of a batch as plain int arrays (no per-pair Python objects): what every call site
+    below except refined_sequences_batch needs from ``Aligner.align``."""
+    rec, _ = ssw_wrap.align_pairs(refs, queries, match, mismatch, gap_open, gap_extend, device=device,
+                                  need_cigar=False, _shared_ref=shared_ref, as_records=True)
+    if len(rec) and ((rec["status"] & 0xff) != 0).any():
+        raise ssw_wrap.SSWCudaError("alignment refused for %d pair(s)" % int(((rec["status"] & 0xff) != 0).sum()))
+    return (rec["score1"].astype(np.int64), rec["ref_begin1"].astype(np.int64), rec["ref_end1"].astype(np.int64),
+            rec["read_begin1"].astype(np.int64), rec["read_end1"].astype(np.int64))
+
+
 def revcomp(seq):
     """CIRI_long/utils.py revcomp"""
     return seq.translate(_COMP)[::-1]
@@ -51,21 +62,23 @@ def align_clip_segments_batch(items, device=0):
             out[k] = (circ[hit.q_st:] + circ[:hit.q_st], hit.r_st - 1, hit.r_en, (None, None, st_clip + en_clip))
     # phase 2: one device batch with the find_bsj scoring (match=1, mismatch=1, gap_open=1, gap_extend=1);
     # only coordinates are consumed, so the CIGAR pass is skipped
-    results = ssw_wrap.align_pairs(refs, queries, 1, 1, 1, 1, device=device, need_cigar=False) if owners else []
-    for k, align_res in zip(owners, results):
+    if owners:
+        _, rb, re_, qb, qe = _coords(refs, queries, 1, 1, 1, 1, device)
+    for n, k in enumerate(owners):
+        ref_begin, ref_end, query_begin, query_end = int(rb[n]), int(re_[n]), int(qb[n]), int(qe[n])
         circ, hit, window, tmp_start, tmp_end = items[k]
         clip_seq = circ[hit.q_en:] + circ[:hit.q_st]
         if hit.strand > 0:
-            clip_r_st, clip_r_en = tmp_start + align_res.ref_begin, tmp_start + align_res.ref_end
+            clip_r_st, clip_r_en = tmp_start + ref_begin, tmp_start + ref_end
             moved = clip_r_st < hit.r_st
         else:
-            clip_r_st, clip_r_en = tmp_end - align_res.ref_end, tmp_end - align_res.ref_begin
+            clip_r_st, clip_r_en = tmp_end - ref_end, tmp_end - ref_begin
             moved = clip_r_en > hit.r_en
         if moved:
-            clipped_circ = clip_seq[align_res.query_begin:] + circ[hit.q_st:hit.q_en] + clip_seq[:align_res.query_begin]
+            clipped_circ = clip_seq[query_begin:] + circ[hit.q_st:hit.q_en] + clip_seq[:query_begin]
         else:
             clipped_circ = circ[hit.q_st:] + circ[:hit.q_st]
-        clip_base = hit.q_st + len(circ) - hit.q_en - (align_res.query_end - align_res.query_begin) + 1
+        clip_base = hit.q_st + len(circ) - hit.q_en - (query_end - query_begin) + 1
         out[k] = (clipped_circ, min(hit.r_st, clip_r_st) - 1, max(hit.r_en, clip_r_en), (clip_r_st, clip_r_en, clip_base))
     return out
 
@@ -81,10 +94,11 @@ def junc_score_batch(genomic_spans, junc_seq_lists, device=0):
         doubled = span * 2
         for s in seqs:
             refs.append(doubled); queries.append(s); owner.append(i)
-    res = ssw_wrap.align_pairs(refs, queries, 10, 4, 8, 2, device=device, need_cigar=False) if refs else []
     sums = np.zeros(len(genomic_spans)); cnt = np.zeros(len(genomic_spans))
-    for i, r in zip(owner, res):
-        sums[i] += r.score; cnt[i] += 1
+    if refs:
+        score = _coords(refs, queries, 10, 4, 8, 2, device)[0]
+        np.add.at(sums, owner, score)
+        np.add.at(cnt, owner, 1)
     return (sums / np.maximum(cnt, 1)).tolist()
 
 
@@ -98,8 +112,11 @@ def curate_junction_batch(candidates, junc, distance=None, device=0):
     Returns ``sorted([(i, j, avg_score)], key=score)`` like the reference."""
     from operator import itemgetter
     refs = [c[2] for c in candidates]
-    res = ssw_wrap.align_pairs(refs, [junc] * len(refs), 10, 4, 8, 2, device=device, need_cigar=False) if refs else []
-    pieces = [junc[alignment.query_begin:alignment.query_end] for alignment in res]     # avg_score, collapse.py:156-158
+    if refs:
+        _, _, _, qb, qe = _coords(refs, [junc] * len(refs), 10, 4, 8, 2, device)
+        pieces = [junc[int(b):int(e)] for b, e in zip(qb, qe)]                          # avg_score, collapse.py:156-158
+    else:
+        pieces = []
     if distance is None:
         from .distance import distance_batch
         dists = distance_batch(refs, pieces, device) if refs else []
@@ -165,15 +182,15 @@ def cluster_junction_seqs_batch(clusters, device=0):
             raise ValueError("cluster %d has no query reads (the reference fails on max([]) here)" % c)
         for q in qs:
             refs.append(ref_seq[:50]); queries.append(q); owner.append(c)
-    res = ssw_wrap.align_pairs(refs, queries, 10, 4, 8, 2, device=device, need_cigar=False)
+    ref_begin = _coords(refs, queries, 10, 4, 8, 2, device)[1]
     head = [[] for _ in clusters]
-    for c, r in zip(owner, res):
-        head[c].append(r.ref_begin)
+    for c, rb in zip(owner, ref_begin):
+        head[c].append(int(rb))
     templates = [transform_seq(ref_seq, max(h)) for (ref_seq, _), h in zip(clusters, head)]
-    res = ssw_wrap.align_pairs([templates[c] for c in owner], queries, 10, 4, 8, 2, device=device, need_cigar=False)
+    query_begin = _coords([templates[c] for c in owner], queries, 10, 4, 8, 2, device)[3]
     out = [(t, [get_junc_seq(t, -max(h) // 2, 25)]) for t, h in zip(templates, head)]
-    for c, q, r in zip(owner, queries, res):
-        out[c][1].append(get_junc_seq(transform_seq(q, r.query_begin), -max(head[c]) // 2, 25))
+    for c, q, qb in zip(owner, queries, query_begin):
+        out[c][1].append(get_junc_seq(transform_seq(q, int(qb)), -max(head[c]) // 2, 25))
     return out
 
 
@@ -203,6 +220,5 @@ def exon_scores_batch(consensus_seq, exon_pair_seqs, device=0):
     exon-pair sequence against the isoform consensus.  Returns ``ref_end - ref_begin`` per candidate."""
     if not exon_pair_seqs:
         return []
-    res = ssw_wrap.align_pairs([consensus_seq] * len(exon_pair_seqs), exon_pair_seqs, 10, 4, 8, 2, device=device,
-                               need_cigar=False, _shared_ref=True)
-    return [r.ref_end - r.ref_begin for r in res]
+    _, rb, re_, _, _ = _coords([consensus_seq] * len(exon_pair_seqs), exon_pair_seqs, 10, 4, 8, 2, device, shared_ref=True)
+    return [int(e - b) for b, e in zip(rb, re_)]
