@@ -95,6 +95,12 @@ struct ssw_batch {
     unsigned char* d_wscr = nullptr;                 // CIGAR pass, wide instance (few pairs, big direction matrices)
     long long wstride = 0, wdir = 0;
     int wblocks = 0;
+    // CIGAR pass, throughput instance (ssw_tband.cu): one pair per lane, used for large batches
+    bool use_tband = false;
+    bool no_cigar = false;                           // (flag & 4) with filterd < 0: no pair can pass the CIGAR gate (ssw.c:850)
+    TbandPlan tplan;
+    unsigned char* d_tscr = nullptr;
+    int32_t *d_tlists = nullptr, *d_tbins = nullptr; // keys | sorted | list a | list b ;  bin_count | bin_base | seg | counts
     uint32_t* d_cigar = nullptr;
     long long cigar_cap = 0, cigar_worst = 0;
     unsigned long long* d_cigar_used = nullptr;
@@ -158,6 +164,7 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_idx4, fs); dev_free(b->d_meta, fs);
     dev_free(b->d_col_off, fs); dev_free(b->d_col_pool, fs); dev_free(b->d_pair_key, fs); dev_free(b->d_pair_left, fs);
     dev_free(b->d_task, fs); dev_free(b->d_task_meta, fs); dev_free(b->d_rtask, fs); dev_free(b->d_rres, fs);
+    dev_free(b->d_tscr, fs); dev_free(b->d_tlists, fs); dev_free(b->d_tbins, fs);
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
@@ -289,17 +296,33 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         CU_TRY(dev_alloc_t(&b->d_sscr[cls], (size_t)(blocks * SCORE_WARPS * b->sstride[cls]), st));
     }
     // CIGAR stage scratch and output
-    if (b->sc.flag != 0) {
+    b->no_cigar = (b->sc.flag & 4) != 0 && b->sc.filterd < 0;              // begin coordinates only: nothing passes ssw.c:850
+    if (b->sc.flag != 0 && !b->no_cigar) {
         b->bstage = cap_q + cap_r + 16;
         const long long rows = std::min(cap_q, cap_r + cap_q);           // rows of the trimmed rectangle <= query length
-        // narrow instance: row stride <= 128 bytes; wide instance: up to 1024 diagonals (wider bands, or
-        // longer reads, are re-run from ssw_batch_fetch with a scratch sized for them)
-        b->bdir = std::max<long long>(65536, 128LL * rows);
-        b->bstride = ((long long)b->bstage * 4 + b->bdir + 255) & ~255LL;
-        long long blocks = std::min<long long>((long long)b->sms * 4, (n + BAND_WARPS - 1) / BAND_WARPS);
-        blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->bstride * BAND_WARPS)));
-        b->bblocks = (int)blocks;
-        CU_TRY(dev_alloc_t(&b->d_bscr, (size_t)(blocks * BAND_WARPS * b->bstride), st));
+        // large batches: one pair per lane (ssw_tband.cu); small ones: one pair per warp (ssw_band.cu)
+        long tband_min = 16384;
+        if (const char* e = getenv("SSW_CUDA_TBAND_MIN")) tband_min = atol(e);
+        b->use_tband = n >= tband_min;
+        long long blocks = 0;
+        if (b->use_tband) {
+            long long budget = SCRATCH_BUDGET;
+            if (const char* e = getenv("SSW_CUDA_TBAND_BUDGET_MB")) { const long v = atol(e); if (v > 0) budget = (long long)v << 20; }
+            CU_TRY(tband_plan(b->device, b->sms, b->max_q, budget, &b->tplan));
+            CU_TRY(tband_configure());
+            CU_TRY(dev_alloc_t(&b->d_tscr, (size_t)b->tplan.scratch_bytes, st));
+            CU_TRY(dev_alloc_t(&b->d_tlists, 4 * nn, st));
+            CU_TRY(dev_alloc_t(&b->d_tbins, 2 * (size_t)TBAND_BINS + 32, st));
+        } else {
+            // narrow instance: row stride <= 128 bytes; wide instance: up to 1024 diagonals (wider bands, or
+            // longer reads, are re-run from ssw_batch_fetch with a scratch sized for them)
+            b->bdir = std::max<long long>(65536, 128LL * rows);
+            b->bstride = ((long long)b->bstage * 4 + b->bdir + 255) & ~255LL;
+            blocks = std::min<long long>((long long)b->sms * 4, (n + BAND_WARPS - 1) / BAND_WARPS);
+            blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->bstride * BAND_WARPS)));
+            b->bblocks = (int)blocks;
+            CU_TRY(dev_alloc_t(&b->d_bscr, (size_t)(blocks * BAND_WARPS * b->bstride), st));
+        }
         b->wdir = std::min<long long>(1024LL * rows + 65536, 64LL << 20);
         b->wstride = ((long long)b->bstage * 4 + b->wdir + 255) & ~255LL;
         blocks = std::min<long long>((long long)b->sms * 2, (n + BAND_WARPS - 1) / BAND_WARPS);
@@ -374,14 +397,32 @@ static int enqueue_cigar_stage(ssw_batch* b, int* launches)
     ba.next_idx = b->d_idx2; ba.next_count = b->count2();
     ba.next2_idx = b->d_idx4; ba.next2_count = b->count3();
     CU_TRY(cudaMemsetAsync(b->count2(), 0, 4 * N_LISTS * 4, st));       // count2, cursor2, count3, cursor3
-    CU_TRY(launch_band(0, ba, b->bblocks, st));
+    if (b->use_tband) {
+        // throughput instance first; what it hands over (bands wider than 126, scores near the 16-bit range,
+        // score-0 pairs) lands in the class-2 list
+        const size_t nn = ((size_t)std::max(b->n, 1) + 16383) & ~(size_t)16383;
+        TbandArgs ta;
+        ta.b = view; ta.sc = b->sc;
+        ta.keys = b->d_tlists; ta.sorted = b->d_tlists + nn;
+        ta.bin_count = b->d_tbins; ta.bin_base = b->d_tbins + TBAND_BINS; ta.seg = b->d_tbins + 2 * TBAND_BINS;
+        ta.next_idx = nullptr; ta.next_count = nullptr;
+        ta.fallback_idx = b->d_idx4; ta.fallback_count = b->count3();
+        ta.scratch = b->d_tscr; ta.scratch_stride = 0; ta.dir_bytes = 0;
+        ta.row_pairs_cap = b->tplan.row_pairs_cap; ta.stage_cap = b->tplan.stage_cap;
+        ta.cigar_buf = b->d_cigar; ta.cigar_cap = b->cigar_cap; ta.cigar_used = b->d_cigar_used;
+        int32_t* cnt = b->d_tbins + 2 * TBAND_BINS + 16;
+        CU_TRY(launch_tband(ta, b->tplan, ls.idx, ls.count, b->n, b->d_tlists + 2 * nn, b->d_tlists + 3 * nn, cnt, cnt + 1, st, launches));
+    } else {
+        CU_TRY(launch_band(0, ba, b->bblocks, st));
+        ba.scratch = b->d_wscr; ba.scratch_stride = b->wstride; ba.dir_bytes = b->wdir;
+        ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+        CU_TRY(launch_band(1, ba, b->wblocks, st));
+        *launches += 2;
+    }
     ba.scratch = b->d_wscr; ba.scratch_stride = b->wstride; ba.dir_bytes = b->wdir;
-    ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
-    CU_TRY(launch_band(1, ba, b->wblocks, st));
     ba.wl = WorkList{b->d_idx4, nullptr, b->count3(), b->cursor3()};
     CU_TRY(launch_band(2, ba, b->wblocks, st));
     *launches += 1;
-    *launches += 2;
     return SSW_OK;
 }
 
@@ -539,7 +580,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         }
         CU_TRY(cudaEventRecord(b->ev[3], st));
         // ---- CIGAR pass
-        { const int rc = enqueue_cigar_stage(b, &launches); if (rc != SSW_OK) return rc; }
+        if (!b->no_cigar) { const int rc = enqueue_cigar_stage(b, &launches); if (rc != SSW_OK) return rc; }
     }
     else CU_TRY(cudaEventRecord(b->ev[3], st));
     CU_TRY(cudaEventRecord(b->ev[4], st));
@@ -621,13 +662,14 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
     { TraceTimer t2("  fetch: d2h records");
     CU_TRY(cudaMemcpyAsync(b->h_rec.data(), b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st)); }
-    if (b->sc.flag != 0) {
+    const bool cigar_stage = b->sc.flag != 0 && !b->no_cigar;
+    if (cigar_stage) {
         std::vector<int32_t> big;
         for (int32_t p = 0; p < b->n; ++p) if (b->h_rec[p].status & PS_BAND_SCRATCH) big.push_back(p);
         if (!big.empty()) { const int rc = rerun_big_bands(b, big); if (rc != SSW_OK) return rc; }
     }
     unsigned long long used = 0;
-    if (b->sc.flag != 0) {
+    if (cigar_stage) {
         CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         if ((long long)used > b->cigar_cap && b->cigar_cap < b->cigar_worst) {

@@ -136,6 +136,40 @@ constexpr int BAND_WARPS = 8;
 // cls 0: bands up to 128 diagonals; 1: up to 256; 2: everything the others handed over
 cudaError_t launch_band(int cls, const BandArgs& a, int blocks, cudaStream_t st);
 
+// ---- throughput CIGAR pass: one pair per lane (ssw_tband.cu, ssw_tband_core.h)
+struct TbandArgs {
+    BatchView b;
+    Scoring sc;
+    int32_t* keys;                 // per list entry: bin (or -1 = handed over)
+    int32_t* sorted;               // list sorted by (band blocks, row pairs), largest first
+    int32_t* bin_count;            // TB_BINS
+    int32_t* bin_base;             // TB_BINS
+    int32_t* seg;                  // per instance: base[4] | count[4] | cursor[4]
+    int32_t* next_idx;             // pairs whose band doubles: list of the next pass
+    int32_t* next_count;
+    int32_t* fallback_idx;         // pairs handed to ssw_band.cu (class 2 instance)
+    int32_t* fallback_count;
+    unsigned char* scratch;        // per-warp direction words + op staging
+    long long scratch_stride;
+    long long dir_bytes;
+    int32_t row_pairs_cap;         // row pairs the direction scratch of one lane holds
+    int32_t stage_cap;             // ops
+    uint32_t* cigar_buf;
+    long long cigar_cap;
+    unsigned long long* cigar_used;
+};
+struct TbandPlan {
+    int32_t row_pairs_cap, stage_cap;
+    int32_t blocks[4], smem[4];
+    long long dir_bytes[4], stride[4];
+    long long scratch_bytes;
+};
+constexpr int TBAND_BINS = 64 * 256;
+cudaError_t tband_plan(int device, int sms, int max_q, long long budget, TbandPlan* plan);
+cudaError_t tband_configure();
+cudaError_t launch_tband(TbandArgs a, const TbandPlan& plan, const int32_t* in_idx, const int32_t* in_count, int n_max,
+                         int32_t* list_a, int32_t* list_b, int32_t* cnt_a, int32_t* cnt_b, cudaStream_t st, int* launches);
+
 // ---- batched edit distance (edit_distance.cu)
 constexpr int ED_MAXSYM = 16;          // distinct symbols per batch (4-bit codes)
 constexpr int EDIT_THREADS = 128;
