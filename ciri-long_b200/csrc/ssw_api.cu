@@ -312,7 +312,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
             CU_TRY(tband_configure());
             CU_TRY(dev_alloc_t(&b->d_tscr, (size_t)b->tplan.scratch_bytes, st));
             CU_TRY(dev_alloc_t(&b->d_tlists, 4 * nn, st));
-            CU_TRY(dev_alloc_t(&b->d_tbins, 2 * (size_t)TBAND_BINS + 32, st));
+            CU_TRY(dev_alloc_t(&b->d_tbins, 2 * (size_t)TBAND_BINS + 64, st));
         } else {
             // narrow instance: row stride <= 128 bytes; wide instance: up to 1024 diagonals (wider bands, or
             // longer reads, are re-run from ssw_batch_fetch with a scratch sized for them)
@@ -407,19 +407,22 @@ static int enqueue_cigar_stage(ssw_batch* b, int* launches)
         ta.bin_count = b->d_tbins; ta.bin_base = b->d_tbins + TBAND_BINS; ta.seg = b->d_tbins + 2 * TBAND_BINS;
         ta.next_idx = nullptr; ta.next_count = nullptr;
         ta.fallback_idx = b->d_idx4; ta.fallback_count = b->count3();
+        ta.fallback1_idx = b->d_idx2; ta.fallback1_count = b->count2();
+        ta.min_pairs_scale = 16;
+        if (const char* e = getenv("SSW_CUDA_TBAND_SEG_SCALE")) ta.min_pairs_scale = atoi(e);
         ta.scratch = b->d_tscr; ta.scratch_stride = 0; ta.dir_bytes = 0;
         ta.row_pairs_cap = b->tplan.row_pairs_cap; ta.stage_cap = b->tplan.stage_cap;
         ta.cigar_buf = b->d_cigar; ta.cigar_cap = b->cigar_cap; ta.cigar_used = b->d_cigar_used;
-        int32_t* cnt = b->d_tbins + 2 * TBAND_BINS + 16;
+        int32_t* cnt = b->d_tbins + 2 * TBAND_BINS + 32;
         CU_TRY(launch_tband(ta, b->tplan, ls.idx, ls.count, b->n, b->d_tlists + 2 * nn, b->d_tlists + 3 * nn, cnt, cnt + 1, st, launches));
     } else {
         CU_TRY(launch_band(0, ba, b->bblocks, st));
-        ba.scratch = b->d_wscr; ba.scratch_stride = b->wstride; ba.dir_bytes = b->wdir;
-        ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
-        CU_TRY(launch_band(1, ba, b->wblocks, st));
-        *launches += 2;
+        *launches += 1;
     }
     ba.scratch = b->d_wscr; ba.scratch_stride = b->wstride; ba.dir_bytes = b->wdir;
+    ba.wl = WorkList{b->d_idx2, nullptr, b->count2(), b->cursor2()};
+    CU_TRY(launch_band(1, ba, b->wblocks, st));
+    *launches += 1;
     ba.wl = WorkList{b->d_idx4, nullptr, b->count3(), b->cursor3()};
     CU_TRY(launch_band(2, ba, b->wblocks, st));
     *launches += 1;
@@ -718,7 +721,8 @@ static int error_code_of_create()
 }
 
 // One-shot call on host buffers.  Large batches are cut into chunks of SSW_CUDA_CHUNK pairs (default
-// 131072) that run as separate device batches on two alternating streams: the host-to-device copy of chunk
+// 262144: the lane-per-pair CIGAR instance wants batches that fill the machine several times over) that run as
+// separate device batches on alternating streams: the host-to-device copy of chunk
 // k+1 and the device-to-host copy of chunk k-1 overlap the kernels of chunk k (with pinned caller memory;
 // pageable memory still works, the copies then serialise).  Each chunk uploads only the byte range of
 // `seqs` its pairs reference, so a pair-major layout moves every byte once.
@@ -727,14 +731,14 @@ extern "C" int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, 
                                const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap,
                                int64_t* cigar_used)
 {
-    int32_t chunk = 131072;
+    int32_t chunk = 262144;
     if (const char* e = getenv("SSW_CUDA_CHUNK")) { const long v = atol(e); if (v > 0 && v < (1L << 30)) chunk = (int32_t)v; }
     if (cigar_used) *cigar_used = 0;
     if (n_pairs <= 0) return n_pairs == 0 ? SSW_OK : SSW_ERR_ARG;
     // chunks in flight: while the host waits for the oldest one, the kernels of the younger ones keep the
     // SMs busy through each other's launch tails and their uploads overlap
     constexpr int MAX_SLOTS = 4;
-    int slots = 3;
+    int slots = 4;
     if (const char* e = getenv("SSW_CUDA_SLOTS")) { const long v = atol(e); if (v >= 2 && v <= MAX_SLOTS) slots = (int)v; }
     ssw_batch* slot[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     int32_t slot_p0[MAX_SLOTS] = {0, 0, 0, 0};

@@ -144,11 +144,14 @@ struct TbandArgs {
     int32_t* sorted;               // list sorted by (band blocks, row pairs), largest first
     int32_t* bin_count;            // TB_BINS
     int32_t* bin_base;             // TB_BINS
-    int32_t* seg;                  // per instance: base[4] | count[4] | cursor[4]
+    int32_t* seg;                  // per instance: base[8] | count[8] | cursor[8] | handed-over flag[8]
+    int32_t min_pairs_scale;       // 16 = default thresholds for "too few pairs for a launch"; 0 = always launch
     int32_t* next_idx;             // pairs whose band doubles: list of the next pass
     int32_t* next_count;
-    int32_t* fallback_idx;         // pairs handed to ssw_band.cu (class 2 instance)
+    int32_t* fallback_idx;         // pairs handed to ssw_band.cu (class 2 instance: any band width)
     int32_t* fallback_count;
+    int32_t* fallback1_idx;        // pairs handed to ssw_band.cu (class 1 instance: up to 256 diagonals)
+    int32_t* fallback1_count;
     unsigned char* scratch;        // per-warp direction words + op staging
     long long scratch_stride;
     long long dir_bytes;
@@ -160,11 +163,11 @@ struct TbandArgs {
 };
 struct TbandPlan {
     int32_t row_pairs_cap, stage_cap;
-    int32_t blocks[4], smem[4];
-    long long dir_bytes[4], stride[4];
+    int32_t blocks[8], smem[8];
+    long long dir_bytes[8], stride[8];
     long long scratch_bytes;
 };
-constexpr int TBAND_BINS = 64 * 256;
+constexpr int TBAND_BINS = 32 * 256;
 cudaError_t tband_plan(int device, int sms, int max_q, long long budget, TbandPlan* plan);
 cudaError_t tband_configure();
 cudaError_t launch_tband(TbandArgs a, const TbandPlan& plan, const int32_t* in_idx, const int32_t* in_count, int n_max,

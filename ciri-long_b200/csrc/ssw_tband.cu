@@ -23,7 +23,9 @@ namespace sswb {
 using namespace sswt;
 
 constexpr int TBAND_WARPS = 4;                       // warps per CTA
-constexpr int TB_NB_MAX = TB_MAX_STEPS / TB_BLOCK;   // 64 blocks
+constexpr int TB_NB_MAX = TB_MAX_STEPS / TB_BLOCK;   // 32 blocks
+constexpr int TB_INST = 5;                           // shared-memory instances: bands of up to 8/12/16/24/32 blocks
+constexpr int TB_PASSES = 5;                         // band-doubling passes run here; what is left goes to ssw_band.cu
 constexpr int TB_RB_SHIFT = 3, TB_RB_MAX = 255;      // row-pair bins of 8 row pairs
 constexpr int TB_BINS = TB_NB_MAX * (TB_RB_MAX + 1);
 
@@ -32,8 +34,11 @@ __device__ __forceinline__ int tb_bin(int nb, int rowPairs)
     int rb = rowPairs >> TB_RB_SHIFT; if (rb > TB_RB_MAX) rb = TB_RB_MAX;
     return (TB_NB_MAX - nb) * (TB_RB_MAX + 1) + (TB_RB_MAX - rb);            // widest band, then most rows, first
 }
-__host__ __device__ inline int tb_instance_of(int nb) { return nb <= 8 ? 0 : nb <= 16 ? 1 : nb <= 32 ? 2 : 3; }
-__host__ __device__ inline int tb_instance_nb(int inst) { return 8 << inst; }
+__host__ __device__ inline int tb_instance_of(int nb) { return nb <= 8 ? 0 : nb <= 12 ? 1 : nb <= 16 ? 2 : nb <= 24 ? 3 : 4; }
+__host__ __device__ inline int tb_instance_nb(int inst) { return inst == 0 ? 8 : inst == 1 ? 12 : inst == 2 ? 16 : inst == 3 ? 24 : 32; }
+// A launch costs at least one lock-step round of 32 pairs per warp (milliseconds for wide bands), so segments
+// with fewer pairs than this are cheaper in the warp-per-pair instance.
+__host__ __device__ inline int tb_instance_min_pairs(int inst) { return inst == 0 ? 3072 : inst == 1 ? 4096 : inst == 2 ? 6144 : inst == 3 ? 10240 : 16384; }
 
 // Geometry of one pair in pass `pass`: band width, rows.  Returns false if the pair leaves for ssw_band.cu.
 __device__ __forceinline__ bool tb_geometry(const TbandArgs& a, const PairRec* rec, int pass, int& bw, int& readLen, int& refLen)
@@ -52,7 +57,8 @@ __device__ __forceinline__ bool tb_geometry(const TbandArgs& a, const PairRec* r
 __device__ __forceinline__ void tb_hand_over(const TbandArgs& a, PairRec* rec, int pair, int bw, int maxv)
 {
     rec->cigar_len = -bw; rec->cigar_off = maxv;                             // ssw_band.cu: band_pair<CLASS > 0> starts from these
-    a.fallback_idx[atomicAdd(a.fallback_count, 1)] = pair;
+    if (2 * bw + 1 <= 256) a.fallback1_idx[atomicAdd(a.fallback1_count, 1)] = pair;   // class 1: up to 256 diagonals
+    else a.fallback_idx[atomicAdd(a.fallback_count, 1)] = pair;
 }
 
 __global__ void tband_key_kernel(TbandArgs a, int pass, const int32_t* in_idx, const int32_t* in_count)
@@ -97,13 +103,14 @@ __global__ void tband_scan_kernel(TbandArgs a)
         run += c;
     }
     __syncthreads();
-    if (t < 4) {
-        // instance t covers bands of (nbLo, nbHi] blocks = bins [(64 - nbHi) * R, (64 - nbLo) * R)
+    if (t < TB_INST) {
+        // instance t covers bands of (nbLo, nbHi] blocks = bins [(NB_MAX - nbHi) * R, (NB_MAX - nbLo) * R)
         const int nbHi = tb_instance_nb(t), nbLo = t == 0 ? 0 : tb_instance_nb(t - 1);
         const int b0 = (TB_NB_MAX - nbHi) * (TB_RB_MAX + 1), b1 = (TB_NB_MAX - nbLo) * (TB_RB_MAX + 1);
         const int lo = a.bin_base[b0];
         const int hi = b1 < TB_BINS ? a.bin_base[b1] : part[1023];
-        a.seg[t] = lo; a.seg[4 + t] = hi - lo; a.seg[8 + t] = 0;             // base, count, cursor
+        const bool small = hi - lo < a.min_pairs_scale * tb_instance_min_pairs(t) / 16;
+        a.seg[t] = lo; a.seg[8 + t] = small ? 0 : hi - lo; a.seg[16 + t] = 0; a.seg[24 + t] = small ? 1 : 0;   // base, count, cursor, handed over
     }
 }
 
@@ -113,7 +120,13 @@ __global__ void tband_scatter_kernel(TbandArgs a, const int32_t* in_idx, const i
     if (k >= *in_count) return;
     const int bin = a.keys[k];
     if (bin < 0) return;
-    a.sorted[a.bin_base[bin] + atomicAdd(a.bin_count + bin, 1)] = in_idx[k];
+    const int pair = in_idx[k];
+    if (a.seg[24 + tb_instance_of(TB_NB_MAX - bin / (TB_RB_MAX + 1))]) {        // too few pairs for a launch of that instance
+        PairRec* rec = a.b.rec + pair;
+        tb_hand_over(a, rec, pair, -rec->cigar_len, (int)rec->cigar_off);
+        return;
+    }
+    a.sorted[a.bin_base[bin] + atomicAdd(a.bin_count + bin, 1)] = pair;
 }
 
 __global__ void tband_reset_kernel(TbandArgs a, int32_t* count_to_clear)
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
 {
     extern __shared__ unsigned tb_smem[];
     __shared__ int matS[25];
-    const int count = a.seg[4 + inst];
+    const int count = a.seg[8 + inst];
     if (count <= 0) return;
     if (threadIdx.x < 25) matS[threadIdx.x] = a.sc.mat[threadIdx.x];
     __syncthreads();
@@ -141,6 +154,7 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
     unsigned* S = reinterpret_cast<unsigned*>(wsm) + lane;
     unsigned char* ring = wsm + (4 * nbcap + 4) * TB_LANES * 4 + lane;
     int* tab = reinterpret_cast<int*>(wsm + (4 * nbcap + 4) * TB_LANES * 5) + lane;
+    const unsigned tabS = (unsigned)__cvta_generic_to_shared(tab);
     unsigned char* wscr = a.scratch + (size_t)(blockIdx.x * TBAND_WARPS + warp) * a.scratch_stride;
     unsigned* dirs = reinterpret_cast<unsigned*>(wscr) + lane;
     unsigned* stage = reinterpret_cast<unsigned*>(wscr + a.dir_bytes) + lane;
@@ -150,7 +164,7 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
 
     for (;;) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(a.seg + 8 + inst, 32);
+        if (lane == 0) base = atomicAdd(a.seg + 16 + inst, 32);
         base = __shfl_sync(FULL, base, 0);
         if (base >= count) break;
         const bool have = base + lane < count;
@@ -169,11 +183,7 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
         const int NB = __reduce_max_sync(FULL, tb_blocks(J.bw));
         const int rowPairsMax = __reduce_max_sync(FULL, myRowPairs);
         const int RING = 4 * NB;
-        auto refcode = [&](int col) -> unsigned {
-            col = col < 0 ? 0 : (col > J.refLen - 1 ? J.refLen - 1 : col);
-            unsigned c = (unsigned char)J.ref[col];
-            return c > 4u ? 4u : c;
-        };
+        auto refcode = [&](int col) -> unsigned { return tb_ref_code(J, col); };
         for (int k = 0; k < 4 * NB + 4; ++k) S[k * TB_LANES] = B2;
         for (int p = 0; p < RING; ++p) ring[p * TB_LANES] = (unsigned char)refcode(p - J.bw);
         for (int p = 0; p < 4; ++p) ring[(RING + p) * TB_LANES] = ring[p * TB_LANES];
@@ -183,38 +193,45 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
         TbRow R;
         int pos0row = 0;
         unsigned* drow = dirs;
+        unsigned nr0 = tb_read_code(J, 0), nr1 = tb_read_code(J, 1);
         for (int rho = 0; rho < rowPairsMax; ++rho) {
-            tb_row_begin(R, J, rho, S, tab, matS, B2);
-            // blocks in which every lane that still has rows is inside band and rectangle with both halves
-            int lo = R.aL > R.aH ? R.aL : R.aH, hi = R.bL < R.bH ? R.bL : R.bH;
-            if (R.tqL >= 0 || R.tqH >= 0 || hi < lo) { lo = 4 * NB; hi = -1; }
-            if (rho >= myRowPairs) { lo = 0; hi = 4 * NB; }
-            const int head = __reduce_max_sync(FULL, lo), tail = __reduce_min_sync(FULL, hi + 1);
+            // loads of the next row pair's read bases and of the two reference bases that enter the window after
+            // this row pair are issued here and consumed at its end
+            const unsigned r0 = nr0, r1 = nr1;
+            nr0 = tb_read_code(J, 2 * rho + 2); nr1 = tb_read_code(J, 2 * rho + 3);
+            const unsigned cNew0 = refcode(2 * rho + RING - J.bw), cNew1 = refcode(2 * rho + RING + 1 - J.bw);
+            tb_row_begin(R, J, rho, S, tab, tabS, matS, B2, r0, r1);
+            // which blocks need which body (ssw_tband_core.h: tb_row_plan), agreed over the lanes that still have rows
+            TbRowPlan pl = tb_row_plan(R, NB);
+            if (rho >= myRowPairs) { pl.lo = 0; pl.hi = 4 * NB; pl.simple = true; }
+            const int head = __reduce_max_sync(FULL, pl.lo), tail = __reduce_min_sync(FULL, pl.hi + 1);
+            const bool simple = __all_sync(FULL, pl.simple);
             int hb = (head + 3) >> 2, tb = tail >> 2;
             if (tb < hb) { hb = NB; tb = NB; }
             int pos = pos0row;
             int b = 0;
+            if (simple && hb == 1) {
+                drow[0] = tb_block<TB_HEAD>(R, 0, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
+                pos += 4; if (pos >= RING) pos -= RING;
+                b = 1;
+            }
             for (; b < hb; ++b) {
-                drow[b * TB_LANES] = tb_block<true>(R, 4 * b, S, ring + pos * TB_LANES, tab, B2, GO2, GE2, maxv2);
+                drow[b * TB_LANES] = tb_block<TB_ANY>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
             }
             for (; b < tb; ++b) {
-                drow[b * TB_LANES] = tb_block<false>(R, 4 * b, S, ring + pos * TB_LANES, tab, B2, GO2, GE2, maxv2);
+                drow[b * TB_LANES] = tb_block<TB_PLAIN>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
             }
             for (; b < NB; ++b) {
-                drow[b * TB_LANES] = tb_block<true>(R, 4 * b, S, ring + pos * TB_LANES, tab, B2, GO2, GE2, maxv2);
+                drow[b * TB_LANES] = tb_block<TB_TAIL>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
             }
             drow += NB * TB_LANES;
             // the window moves two columns to the right
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int p = pos0row + k;                                    // pos0row is even and < RING
-                const unsigned char c = (unsigned char)refcode(2 * rho + RING + k - J.bw);
-                ring[p * TB_LANES] = c;
-                if (p < 4) ring[(RING + p) * TB_LANES] = c;
-            }
+            ring[pos0row * TB_LANES] = (unsigned char)cNew0;                  // pos0row is even and < RING
+            ring[(pos0row + 1) * TB_LANES] = (unsigned char)cNew1;
+            if (pos0row < 4) { ring[(RING + pos0row) * TB_LANES] = (unsigned char)cNew0; ring[(RING + pos0row + 1) * TB_LANES] = (unsigned char)cNew1; }
             pos0row += 2; if (pos0row >= RING) pos0row -= RING;
             if (rho + 1 == myRowPairs) finalMax = maxv2;
         }
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
         if (have) {
             if (again) {
                 const int bw2 = 2 * J.bw;
-                if (tb_steps(bw2) > TB_MAX_STEPS) tb_hand_over(a, rec, pair, bw2, mx);
+                if (tb_steps(bw2) > TB_MAX_STEPS || pass + 1 >= TB_PASSES) tb_hand_over(a, rec, pair, bw2, mx);
                 else { rec->cigar_len = -bw2; rec->cigar_off = mx; a.next_idx[atomicAdd(a.next_count, 1)] = pair; }
             } else if (fallback) tb_hand_over(a, rec, pair, J.bw, (int)rec->cigar_off);
             else {
@@ -268,10 +285,10 @@ cudaError_t tband_plan(int device, int sms, int max_q, long long budget, TbandPl
     cudaError_t e = cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
     long long worst = 0;
-    for (int inst = 0; inst < 4; ++inst) {
+    for (int inst = 0; inst < TB_INST; ++inst) {
         const int nbcap = tb_instance_nb(inst);
         const int smem = TBAND_WARPS * tband_warp_smem(nbcap);
-        int perSm = (smemMax + 1024) / (smem + 1024); if (perSm > 6) perSm = 6; if (perSm < 1) perSm = 1;
+        int perSm = smemMax / (smem + 1024 + 128); if (perSm > 8) perSm = 8; if (perSm < 1) perSm = 1;   // (+1 KB per CTA reserved by the driver)
         const long long dirBytes = (((long long)rp * nbcap * TB_LANES * 4) + 255) & ~255LL;
         const long long stride = dirBytes + (((long long)plan->stage_cap * TB_LANES * 4 + 255) & ~255LL);
         long long blocks = (long long)sms * perSm;
@@ -303,14 +320,14 @@ cudaError_t launch_tband(TbandArgs a, const TbandPlan& plan, const int32_t* in_i
     const int threads = 256, blocks = (n_max + threads - 1) / threads;
     const int32_t* cur_idx = in_idx; const int32_t* cur_cnt = in_count;
     int32_t* nxt_idx = list_a; int32_t* nxt_cnt = cnt_a;
-    for (int pass = 0; pass < 7; ++pass) {
+    for (int pass = 0; pass < TB_PASSES; ++pass) {
         tband_reset_kernel<<<(TB_BINS + 255) / 256, 256, 0, st>>>(a, nxt_cnt);
         tband_key_kernel<<<blocks, threads, 0, st>>>(a, pass, cur_idx, cur_cnt);
         tband_scan_kernel<<<1, 1024, 0, st>>>(a);
         tband_scatter_kernel<<<blocks, threads, 0, st>>>(a, cur_idx, cur_cnt);
         *launches += 4;
         a.next_idx = nxt_idx; a.next_count = nxt_cnt;
-        for (int inst = 3; inst >= 0; --inst) {
+        for (int inst = TB_INST - 1; inst >= 0; --inst) {
             TbandArgs x = a;
             x.scratch_stride = plan.stride[inst]; x.dir_bytes = plan.dir_bytes[inst];
             tband_kernel<<<plan.blocks[inst], TBAND_WARPS * 32, plan.smem[inst], st>>>(x, inst, tb_instance_nb(inst), pass);

@@ -31,7 +31,7 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define TB_HD __host__ __device__ __forceinline__
+#define TB_HD __device__ __forceinline__
 #else
 #define TB_HD inline
 #endif
@@ -39,13 +39,13 @@
 namespace sswt {
 
 constexpr int TB_BLOCK = 4;                     // steps per direction word
-constexpr int TB_MAX_STEPS = 256;               // widest instance: 2*bw + 3 <= 256
+constexpr int TB_MAX_STEPS = 128;               // widest instance: 2*bw + 3 <= 128 (wider bands fill a whole warp: ssw_band.cu)
 constexpr int TB_SCORE_LIMIT = 32000;           // score1 + bias must stay below the s16 range
 
 // ---- packed primitives ---------------------------------------------------------------------------------
 TB_HD unsigned tb_prmt(unsigned a, unsigned b, unsigned sel)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
     unsigned v; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(a), "r"(b), "r"(sel)); return v;
 #else
     const unsigned long long src = ((unsigned long long)b << 32) | a;
@@ -57,7 +57,7 @@ TB_HD unsigned tb_prmt(unsigned a, unsigned b, unsigned sel)
 
 TB_HD unsigned tb_max2(unsigned a, unsigned b)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
     unsigned v; asm("max.s16x2 %0, %1, %2;" : "=r"(v) : "r"(a), "r"(b)); return v;
 #else
     const short al = (short)(a & 0xffff), ah = (short)(a >> 16), bl = (short)(b & 0xffff), bh = (short)(b >> 16);
@@ -69,7 +69,7 @@ TB_HD unsigned tb_max2(unsigned a, unsigned b)
 template <unsigned IMM_LO, unsigned IMM_HI>
 TB_HD unsigned tb_max2_b_wins(unsigned a, unsigned b, unsigned& acc)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
     unsigned r;
     asm("{\n\t.reg .pred pl, ph;\n\t.reg .s16 r0, r1, a0, a1;\n\t"
         "max.s16x2 %0, %2, %3;\n\t"
@@ -93,7 +93,7 @@ TB_HD unsigned tb_max2_b_wins(unsigned a, unsigned b, unsigned& acc)
 template <unsigned IMM_LO, unsigned IMM_HI>
 TB_HD unsigned tb_max2_a_wins(unsigned a, unsigned b, unsigned& acc)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
     unsigned r;
     asm("{\n\t.reg .pred pl, ph;\n\t.reg .s16 r0, r1, a0, a1;\n\t"
         "max.s16x2 %0, %2, %3;\n\t"
@@ -113,6 +113,24 @@ TB_HD unsigned tb_max2_a_wins(unsigned a, unsigned b, unsigned& acc)
 #endif
 }
 
+// ---- per-lane score tables: tab[c] = s(c, read[i0]) sign-extended, tab[5+c] = s(c, read[i0+1]) << 16 ------
+// On the device the table is addressed through the 32-bit shared window, so that the address of an entry is
+// one multiply-add (FMA pipe) and the second table is an immediate offset.
+#if defined(__CUDACC__)
+typedef unsigned TbAddr;
+__device__ __forceinline__ TbAddr tb_tab_addr(const unsigned tabS, const unsigned c)
+{ unsigned v; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(c), "r"(128u), "r"(tabS)); return v; }
+__device__ __forceinline__ unsigned tb_tab_lo(const TbAddr a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned tb_tab_hi(const TbAddr a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1+640];" : "=r"(v) : "r"(a)); return v; }
+typedef unsigned TbTab;
+#else
+typedef const int* TbAddr;
+inline TbAddr tb_tab_addr(const int* tab, const unsigned c) { return tab + c * 32; }
+inline unsigned tb_tab_lo(const TbAddr a) { return (unsigned)a[0]; }
+inline unsigned tb_tab_hi(const TbAddr a) { return (unsigned)a[5 * 32]; }
+typedef const int* TbTab;
+#endif
+
 // ---- per-lane state -------------------------------------------------------------------------------------
 // Shared-memory arrays are passed as pointers already offset to the lane; consecutive positions are
 // TB_LANES elements apart.
@@ -131,7 +149,7 @@ struct TbRow {                       // state of the current row pair
     int32_t aL, bL, aH, bH;          // valid step ranges [a, b] of the low / high row (time index t)
     int32_t tqL, tqH;                // step whose vertical neighbour is zeroed (ssw.c:595-596), -1 = none
     unsigned Hl, Fl, Eprev, Hd;      // H / F of the previous step (left neighbours), E of it, diagonal
-    unsigned cPrevAddr;              // table address of the previous reference base (high row's score)
+    TbAddr cPrevAddr;                // table address of the previous reference base (high row's score)
 };
 
 TB_HD int tb_steps(int bw) { return 2 * bw + 3; }                           // 2w+1 diagonals + 2 of skew
@@ -154,15 +172,20 @@ TB_HD int tb_row_quirk(int i, int readLen, int refLen, int w)
 }
 
 // One step.  S: H|E<<16 of the row above the pair, indexed by diagonal (in place: this step reads t+1 and
-// writes t-2).  ringB: reference codes by band position, bytes.  tab: per-lane score tables,
-// tab[c] = s(c, read[i0]) sign-extended, tab[5+c] = s(c, read[i0+1]) << 16.
-template <int P, bool MASKED>
-TB_HD void tb_step(TbRow& R, const int t, unsigned* S, const unsigned char* ringPos, const int* tab,
+// writes t-2).  ringB: reference codes by band position, bytes.  MODE says what can be outside band or
+// rectangle in this block (the driver picks it per block for the whole warp):
+//   TB_PLAIN  nothing: both rows inside for every lane
+//   TB_HEAD   block 0 of a row pair whose band starts at diagonal 0: only the high row's two steps of skew
+//   TB_TAIL   the last blocks: a step is valid iff t <= b (the row has begun in every lane)
+//   TB_ANY    anything, including the zeroed vertical neighbour of ssw.c:595-596
+enum { TB_PLAIN = 0, TB_ANY = 1, TB_HEAD = 2, TB_TAIL = 3 };
+template <int P, int MODE>
+TB_HD void tb_step(TbRow& R, const int t, unsigned* S, const unsigned char* ringPos, const TbTab tab,
                    const unsigned B2, const unsigned GO2, const unsigned GE2, unsigned& dirw, unsigned& maxv2)
 {
     unsigned w = S[(t + 1) * TB_LANES];
     unsigned Hprev = R.Hl, Eprev = R.Eprev;
-    if (MASKED) {
+    if (MODE == TB_ANY) {
         if (t == R.tqL) w = B2;                                   // low row: zeroed vertical neighbour
         if (t == R.tqH) { Hprev = (Hprev & 0xffff0000u) | (B2 & 0xffffu); Eprev = (Eprev & 0xffff0000u) | (B2 & 0xffffu); }
     }
@@ -176,39 +199,62 @@ TB_HD void tb_step(TbRow& R, const int t, unsigned* S, const unsigned char* ring
     const unsigned f1 = tb_max2(F, B2);
     const unsigned gb = tb_max2_a_wins<8u << (8 * P), 8u << (8 * P + 4)>(f1, E, dirw);       // F wins ties against E
     // substitution scores: low row against ref[j], high row against ref[j-1]
-    const unsigned cAddr = (unsigned)ringPos[P * TB_LANES] * TB_LANES;
-    const unsigned dg = R.Hd + (unsigned)tab[cAddr] + (unsigned)tab[R.cPrevAddr + 5 * TB_LANES];
+    const TbAddr cAddr = tb_tab_addr(tab, (unsigned)ringPos[P * TB_LANES]);
+    const unsigned dg = R.Hd + tb_tab_lo(cAddr) + tb_tab_hi(R.cPrevAddr);
     R.cPrevAddr = cAddr;
     unsigned H = tb_max2_b_wins<4u << (8 * P), 4u << (8 * P + 4)>(dg, gb, dirw);             // diagonal wins ties
     bool hiValid = true;
-    if (MASKED) {
-        const bool loValid = (unsigned)(t - R.aL) <= (unsigned)(R.bL - R.aL) && R.bL >= R.aL;
-        hiValid = (unsigned)(t - R.aH) <= (unsigned)(R.bH - R.aH) && R.bH >= R.aH;
+    if (MODE == TB_ANY || MODE == TB_TAIL) {
+        bool loValid;
+        if (MODE == TB_ANY) {
+            loValid = (unsigned)(t - R.aL) <= (unsigned)(R.bL - R.aL) && R.bL >= R.aL;
+            hiValid = (unsigned)(t - R.aH) <= (unsigned)(R.bH - R.aH) && R.bH >= R.aH;
+        } else { loValid = t <= R.bL; hiValid = t <= R.bH; }
         const unsigned m = (loValid ? 0xffffu : 0u) | (hiValid ? 0xffff0000u : 0u);
         H = (H & m) | (B2 & ~m); E = (E & m) | (B2 & ~m); F = (F & m) | (B2 & ~m);
     }
+    if (MODE == TB_HEAD && P < 2) {
+        hiValid = false;
+        H = (H & 0xffffu) | (B2 & 0xffff0000u); E = (E & 0xffffu) | (B2 & 0xffff0000u); F = (F & 0xffffu) | (B2 & 0xffff0000u);
+    }
     maxv2 = tb_max2(maxv2, H);
     // the high row is the one the next row pair reads back
-    if (!MASKED || hiValid) S[(t - 2) * TB_LANES] = tb_prmt(H, E, 0x7632u);       // (unmasked blocks start at t >= 4)
+    if (hiValid) S[(t - 2) * TB_LANES] = tb_prmt(H, E, 0x7632u);
     R.Hd = Hup;
     R.Hl = H; R.Eprev = E; R.Fl = F;
 }
 
 // One block of TB_BLOCK steps; returns the direction word.
-template <bool MASKED>
-TB_HD unsigned tb_block(TbRow& R, const int t0, unsigned* S, const unsigned char* ringPos, const int* tab,
+template <int MODE>
+TB_HD unsigned tb_block(TbRow& R, const int t0, unsigned* S, const unsigned char* ringPos, const TbTab tab,
                         const unsigned B2, const unsigned GO2, const unsigned GE2, unsigned& maxv2)
 {
     unsigned dirw = 0;
-    tb_step<0, MASKED>(R, t0 + 0, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
-    tb_step<1, MASKED>(R, t0 + 1, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
-    tb_step<2, MASKED>(R, t0 + 2, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
-    tb_step<3, MASKED>(R, t0 + 3, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
+    tb_step<0, MODE>(R, t0 + 0, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
+    tb_step<1, MODE>(R, t0 + 1, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
+    tb_step<2, MODE>(R, t0 + 2, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
+    tb_step<3, MODE>(R, t0 + 3, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
     return dirw;
 }
 
-// Start of a row pair: ranges, score tables, neighbour state.  matS: the 5x5 matrix as ints.
-TB_HD void tb_row_begin(TbRow& R, const TbJob& J, const int rho, const unsigned* S, int* tab, const int* matS, const unsigned B2)
+// Which blocks of a row pair need which body.  Per lane: the first step from which both rows are inside
+// (lo) and the last one (hi); `simple` = the band starts at diagonal 0 and nothing but the skew is outside at
+// the front.  The driver reduces (max lo, min hi, all simple) over the lanes that still have rows.
+struct TbRowPlan { int lo, hi; bool simple; };
+TB_HD TbRowPlan tb_row_plan(const TbRow& R, const int NB)
+{
+    TbRowPlan p;
+    p.lo = R.aL > R.aH ? R.aL : R.aH;
+    p.hi = R.bL < R.bH ? R.bL : R.bH;
+    p.simple = R.aL == 0 && R.aH == 2 && R.tqL < 0 && R.tqH < 0 && p.hi >= p.lo;
+    if (R.tqL >= 0 || R.tqH >= 0 || p.hi < p.lo) { p.lo = 4 * NB; p.hi = -1; }
+    return p;
+}
+
+// Start of a row pair: ranges, score tables, neighbour state.  matS: the 5x5 matrix as ints; r0, r1: the read
+// bases of the two rows (already clamped to 0..4; the driver loads them one row pair ahead).
+TB_HD void tb_row_begin(TbRow& R, const TbJob& J, const int rho, const unsigned* S, int* tab, const TbTab tabRef, const int* matS,
+                        const unsigned B2, const unsigned r0, const unsigned r1)
 {
     const int i0 = 2 * rho, i1 = i0 + 1;
     int a, b;
@@ -216,18 +262,25 @@ TB_HD void tb_row_begin(TbRow& R, const TbJob& J, const int rho, const unsigned*
     tb_row_range(i1, J.readLen, J.refLen, J.bw, a, b); R.aH = a + 2; R.bH = b + 2;
     const int qL = tb_row_quirk(i0, J.readLen, J.refLen, J.bw), qH = tb_row_quirk(i1, J.readLen, J.refLen, J.bw);
     R.tqL = qL; R.tqH = qH < 0 ? -1 : qH + 2;
-    const int last = J.readLen - 1;
-    // (codes above 4 are never produced by the encoders; they count as N, like in the other kernels)
-    unsigned r0 = (unsigned char)J.read[i0 < last ? i0 : last], r1 = (unsigned char)J.read[i1 < last ? i1 : last];
-    if (r0 > 4u) r0 = 4u;
-    if (r1 > 4u) r1 = 4u;
     for (int c = 0; c < 5; ++c) {
         tab[c * TB_LANES] = matS[c * 5 + r0];
         tab[(5 + c) * TB_LANES] = matS[c * 5 + r1] * 65536;
     }
     R.Hl = B2; R.Fl = B2; R.Eprev = B2;
     R.Hd = (S[0] & 0xffffu) | (B2 & 0xffff0000u);                 // diagonal of (i0, 0) is (i0-1, 0); high row starts outside
-    R.cPrevAddr = 0;                                              // high row's first two steps are outside the band
+    R.cPrevAddr = tb_tab_addr(tabRef, 0);                         // high row's first two steps are outside the band
+}
+TB_HD unsigned tb_read_code(const TbJob& J, int i)
+{
+    const int last = J.readLen - 1;
+    const unsigned c = (unsigned char)J.read[i < last ? i : last];
+    return c > 4u ? 4u : c;                                       // codes above 4 are never produced by the encoders; they count as N
+}
+TB_HD unsigned tb_ref_code(const TbJob& J, int col)
+{
+    col = col < 0 ? 0 : (col > J.refLen - 1 ? J.refLen - 1 : col);
+    const unsigned c = (unsigned char)J.ref[col];
+    return c > 4u ? 4u : c;
 }
 
 // ---- traceback (ssw.c:636-727) ---------------------------------------------------------------------------

@@ -16,7 +16,7 @@ using namespace sswt;
 struct Pair { std::vector<int8_t> q, r; orc_result res; int st; };
 
 static unsigned rng_state = 12345;
-static long g_blocks_masked = 0, g_blocks_plain = 0, g_quirk_rows = 0, g_passes = 0;
+static long g_blocks_masked = 0, g_blocks_plain = 0, g_quirk_rows = 0, g_passes = 0, g_mode[4] = {0, 0, 0, 0};
 static unsigned rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
 
 struct LaneOut { int nOps; std::vector<unsigned> ops; int bwFinal; };
@@ -42,7 +42,7 @@ static void run_warp(std::vector<TbJob>& jobs, const int8_t* mat, int go, int ge
         std::vector<int> tab(10 * 32, 0);
         std::vector<unsigned> dirs((size_t)rowPairsMax * NB * 32, 0);
         std::vector<unsigned> maxv2(n), finalMax(n, 0);
-        auto refcode = [&](const TbJob& J, int col) { col = col < 0 ? 0 : (col > J.refLen - 1 ? J.refLen - 1 : col); return (unsigned char)J.ref[col]; };
+        auto refcode = [&](const TbJob& J, int col) { return (unsigned char)tb_ref_code(J, col); };
         for (int l = 0; l < n; ++l) {
             if (done[l]) continue;
             const TbJob& J = jobs[l];
@@ -52,30 +52,32 @@ static void run_warp(std::vector<TbJob>& jobs, const int8_t* mat, int go, int ge
         }
         std::vector<TbRow> R(n);
         for (int rho = 0; rho < rowPairsMax; ++rho) {
-            int head = 0, tail = 4 * NB;
+            int head = 0, tail = 4 * NB; bool simple = true;
             for (int l = 0; l < n; ++l) {
                 if (done[l]) continue;
-                tb_row_begin(R[l], jobs[l], rho, &S[l], &tab[l], matS, B2);
+                tb_row_begin(R[l], jobs[l], rho, &S[l], &tab[l], &tab[l], matS, B2, tb_read_code(jobs[l], 2 * rho), tb_read_code(jobs[l], 2 * rho + 1));
                 if (rho < (jobs[l].readLen + 1) / 2) {
-                    const TbRow& r = R[l];
-                    int lo = std::max(r.aL, r.aH), hi = std::min(r.bL, r.bH);
-                    if (r.tqL >= 0 || r.tqH >= 0) ++g_quirk_rows;
-                    if (r.tqL >= 0 || r.tqH >= 0 || hi < lo) { lo = 4 * NB; hi = -1; }
-                    head = std::max(head, lo); tail = std::min(tail, hi + 1);
+                    const TbRowPlan pl = tb_row_plan(R[l], NB);
+                    if (R[l].tqL >= 0 || R[l].tqH >= 0) ++g_quirk_rows;
+                    head = std::max(head, pl.lo); tail = std::min(tail, pl.hi + 1); simple = simple && pl.simple;
                 }
             }
             int hb = (head + 3) / 4, tb = tail / 4;
             if (tb < hb) { hb = NB; tb = NB; }
+            const bool headMode = simple && hb == 1;
             const int pos0row = (2 * rho) % RING;
             for (int b = 0; b < NB; ++b) {
                 const int pos0 = (pos0row + 4 * b) % RING;
-                const bool masked = b < hb || b >= tb;
-                (masked ? g_blocks_masked : g_blocks_plain) += 1;
+                const int mode = b < hb ? (headMode ? TB_HEAD : TB_ANY) : b < tb ? TB_PLAIN : (hb == NB ? TB_ANY : TB_TAIL);
+                (mode != TB_PLAIN ? g_blocks_masked : g_blocks_plain) += 1; g_mode[mode] += 1;
                 for (int l = 0; l < n; ++l) {
                     if (done[l]) continue;
                     unsigned w;
-                    if (masked) w = tb_block<true>(R[l], 4 * b, &S[l], &ring[(size_t)pos0 * 32 + l], &tab[l], B2, GO2, GE2, maxv2[l]);
-                    else w = tb_block<false>(R[l], 4 * b, &S[l], &ring[(size_t)pos0 * 32 + l], &tab[l], B2, GO2, GE2, maxv2[l]);
+                    const unsigned char* rp = &ring[(size_t)pos0 * 32 + l];
+                    if (mode == TB_ANY) w = tb_block<TB_ANY>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
+                    else if (mode == TB_HEAD) w = tb_block<TB_HEAD>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
+                    else if (mode == TB_TAIL) w = tb_block<TB_TAIL>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
+                    else w = tb_block<TB_PLAIN>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
                     dirs[((size_t)rho * NB + b) * 32 + l] = w;
                 }
             }
@@ -117,14 +119,15 @@ int main(int argc, char** argv)
         int8_t mat[25];
         for (int a = 0; a < 5; ++a) for (int b = 0; b < 5; ++b) mat[a * 5 + b] = (a == 4 || b == 4) ? 0 : (a == b ? sc[0] : -sc[1]);
         const int n = 1 + rnd() % 32;
-        const int family = rnd() % 4;        // 0 tiny, 1 medium, 2 C2-like, 3 short-vs-long (wide bands)
+        const int family = rnd() % 5;        // 0 tiny, 1 medium, 2 C2-like, 3 short-vs-long (wide bands), 4 one length per warp (sorted-list case)
+        const int m4 = 40 + rnd() % 400;
         std::vector<Pair> pairs(n);
         for (auto& p : pairs) {
-            int m = family == 0 ? 8 + rnd() % 50 : family == 1 ? 60 + rnd() % 200 : family == 2 ? 250 + rnd() % 300 : 20 + rnd() % 120;
+            int m = family == 4 ? m4 : family == 0 ? 8 + rnd() % 50 : family == 1 ? 60 + rnd() % 200 : family == 2 ? 250 + rnd() % 300 : 20 + rnd() % 120;
             std::vector<int8_t> core(m);
             for (auto& c : core) c = rnd() % 4;
             p.q.clear(); p.r.clear();
-            const int fl = rnd() % 30, fr = rnd() % 30;
+            const int fl = family == 4 ? 5 : rnd() % 30, fr = family == 4 ? 5 : rnd() % 30;
             for (int k = 0; k < fl; ++k) p.r.push_back(rnd() % 4);
             const int err = family == 3 ? 25 : (rnd() % 3 == 0 ? 20 : 8);
             for (int k = 0; k < m; ++k) {
@@ -176,6 +179,6 @@ int main(int argc, char** argv)
         done += n;
     }
     printf("tband host check: %ld pairs checked, %ld mismatches, %ld skipped, %ld traceback-error cases\n", checked, bad, skipped, tberr);
-    printf("  warp passes %ld, blocks masked %ld plain %ld, quirk row pairs %ld\n", g_passes, g_blocks_masked, g_blocks_plain, g_quirk_rows);
+    printf("  warp passes %ld, blocks masked %ld plain %ld, quirk row pairs %ld; modes plain/any/head/tail %ld/%ld/%ld/%ld\n", g_passes, g_blocks_masked, g_blocks_plain, g_quirk_rows, g_mode[0], g_mode[1], g_mode[2], g_mode[3]);
     return bad ? 1 : 0;
 }
