@@ -13,7 +13,9 @@ import numpy as np
 
 from . import ssw_wrap
 
-_COMP = str.maketrans("ATCGNatcgn", "TAGCNtagcn")
+# CIRI_long/utils.py:118-120: upper-case A/T/C/G only -- lower-case (soft-masked) bases are reversed but NOT
+# complemented by the reference, and the results must stay identical to it
+_COMP = str.maketrans("ATCG", "TAGC")
 
 Hit = namedtuple("Hit", "q_st q_en r_st r_en strand")
 
@@ -23,14 +25,15 @@ def _coords(refs, queries, match, mismatch, gap_open, gap_extend, device, shared
     below except refined_sequences_batch needs from ``Aligner.align``."""
     rec, _ = ssw_wrap.align_pairs(refs, queries, match, mismatch, gap_open, gap_extend, device=device,
                                   need_cigar=False, _shared_ref=shared_ref, as_records=True)
-    if len(rec) and ((rec["status"] & 0xff) != 0).any():
-        raise ssw_wrap.SSWCudaError("alignment refused for %d pair(s)" % int(((rec["status"] & 0xff) != 0).sum()))
+    # (status 1 only concerns the CIGAR -- the traceback left the band --, coordinates are exact)
+    if len(rec) and ((rec["status"] & 0xff) > 1).any():
+        raise ssw_wrap.SSWCudaError("alignment refused for %d pair(s)" % int(((rec["status"] & 0xff) > 1).sum()))
     return (rec["score1"].astype(np.int64), rec["ref_begin1"].astype(np.int64), rec["ref_end1"].astype(np.int64),
             rec["read_begin1"].astype(np.int64), rec["read_end1"].astype(np.int64))
 
 
 def revcomp(seq):
-    """CIRI_long/utils.py revcomp"""
+    """CIRI_long/utils.py:118-120 (same translation table, lower-case letters pass through unchanged)"""
     return seq.translate(_COMP)[::-1]
 
 
@@ -209,7 +212,9 @@ def refined_sequences_batch(items, device=0):
     for (c, k), alignment in zip(owner, res):
         junc, reads = items[c]
         read_id, seq = reads[k]
-        tmp_pos = find_alignment_pos(alignment, len(junc) // 2)
+        # no CIGAR (alignment refused, or its traceback left the band and the reference's CIGAR is undefined):
+        # the read keeps its rotation, like a junction position outside the alignment
+        tmp_pos = None if alignment is None or alignment.cigar_string is None else find_alignment_pos(alignment, len(junc) // 2)
         out[c][k] = (read_id, seq) if tmp_pos is None else (read_id, transform_seq(seq, tmp_pos % len(seq)))
     return out
 

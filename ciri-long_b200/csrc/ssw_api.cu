@@ -13,7 +13,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ssw_cuda.h"
@@ -42,23 +44,44 @@ extern "C" const char* ssw_cuda_last_error(void) { return g_last_error.c_str(); 
         }                                                                                     \
     } while (0)
 
-// Device memory comes from the stream-ordered allocator with an unbounded release threshold, so that
-// repeated batches (the e2e path creates one per chunk) reuse their buffers instead of paying cudaMalloc.
+// Device memory comes from a stream-ordered pool that belongs to this library (one per device, created on first
+// use, thread-safe): repeated batches (the one-shot call creates one per chunk) get their buffers back from the
+// pool instead of paying cudaMalloc, and the process-wide default pool of other CUDA users is left alone.
+// ssw_cuda_trim_pools() hands the cached memory back to the driver.
+static cudaMemPool_t g_pool[64];
+static std::once_flag g_pool_once[64];
+static cudaMemPool_t lib_pool(int dev)
+{
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::call_once(g_pool_once[dev], [dev]() {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;                       // keep freed blocks cached for the next batch
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            g_pool[dev] = pool;
+        } else { cudaGetLastError(); g_pool[dev] = nullptr; }
+    });
+    return g_pool[dev];
+}
 static cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t st)
 {
-    static bool pool_ready[64] = {false};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !pool_ready[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        pool_ready[dev] = true;
-    }
+    cudaMemPool_t pool = lib_pool(dev);
+    if (pool) return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, st);
     return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+extern "C" int ssw_cuda_trim_pools(void)
+{
+    for (int dev = 0; dev < 64; ++dev) if (g_pool[dev]) cudaMemPoolTrimTo(g_pool[dev], 0);
+    return SSW_OK;
 }
 template <typename T> static cudaError_t dev_alloc_t(T** p, size_t count, cudaStream_t st) { return dev_alloc((void**)p, count * sizeof(T), st); }
 static void dev_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
@@ -968,11 +991,11 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
         fprintf(stderr, "libssw_cuda: %s\n", g_last_error.c_str());
         return nullptr;
     }
-    if ((res.status & 0xff) == SSW_PAIR_TRACEBACK_ERR) {
-        fprintf(stderr, "Trace back error.\n");
-        return nullptr;
-    }
-    if ((res.status & 0xff) != SSW_PAIR_OK) {
+    // The traceback left the band (ssw.c:642-673 then indexes direction bytes no band pass wrote and the
+    // reference's CIGAR is whatever that heap memory yields): score and coordinates are exact and are returned,
+    // the CIGAR is empty (cigar == NULL, cigarLen == 0) instead of undefined.
+    if ((res.status & 0xff) == SSW_PAIR_TRACEBACK_ERR) res.cigar_len = 0;
+    else if ((res.status & 0xff) != SSW_PAIR_OK) {
         fprintf(stderr, "libssw_cuda: this pair needs a code path the device library does not provide.\n");
         return nullptr;
     }

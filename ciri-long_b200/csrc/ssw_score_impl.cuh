@@ -32,6 +32,7 @@
 //          skipped by selecting the hand-off from row K-2), and the reference's pad rows are simply the
 //          tail of the last segment.
 #include <stdio.h>
+#include <atomic>
 #include <type_traits>
 #include "ssw_common.cuh"
 #include "ssw_kernels.h"
@@ -591,13 +592,15 @@ __global__ void __launch_bounds__(score_warps(K) * 32, 1) score_kernel(const Sco
 template <int K, bool TRUNC, bool REV, bool CHUNK>
 static cudaError_t launch_one(const ScoreArgs& a, int blocks, cudaStream_t st)
 {
-    static bool configured[16] = {false};
+    // one-time opt-in to the large dynamic shared memory, per device; callers may come from several host
+    // threads (one per GPU in ssw_align_batch_multi), so the flags are atomics and a repeated call is harmless
+    static std::atomic<bool> configured[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(score_kernel<K, TRUNC, REV, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCORE_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     score_kernel<K, TRUNC, REV, CHUNK><<<blocks, score_warps(K) * 32, SCORE_SMEM_BYTES, st>>>(a);
     return cudaGetLastError();

@@ -487,7 +487,9 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
     out = []
     for i in range(len(queries)):
         r = rec[i]
-        if (r['status'] & 0xff) != 0:
+        # status 1 = the traceback left the band (ssw.c:642-673 reads unwritten direction bytes there): score and
+        # coordinates are exact, the CIGAR is empty -> cigar_string None
+        if (r['status'] & 0xff) not in (0, 1):
             out.append(None)
             continue
         match_len = r['read_end1'] - r['read_begin1'] + 1

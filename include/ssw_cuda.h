@@ -80,7 +80,9 @@ enum {
 /* per-pair status: low byte of ssw_result.status (bits 8.. carry internal stage flags for diagnostics) */
 enum {
     SSW_PAIR_OK = 0,
-    SSW_PAIR_TRACEBACK_ERR = 1, /* the reference would return NULL ("Trace back error", ssw.c:674-682) */
+    SSW_PAIR_TRACEBACK_ERR = 1, /* the traceback left the band: the reference reads direction bytes it never wrote
+                                   (ssw.c:642-673) and returns an undefined CIGAR or NULL ("Trace back error",
+                                   ssw.c:674-682).  Score and coordinates are exact; cigar_len is 0. */
     SSW_PAIR_UNSUPPORTED = 2    /* pair needs a path this build does not provide (reported, never guessed) */
 };
 
@@ -160,6 +162,8 @@ int ssw_cuda_edit_distance_batch(int device, int32_t n_pairs, const uint8_t* seq
                                  const int64_t* x_off, const int32_t* x_len,
                                  const int64_t* y_off, const int32_t* y_len, int32_t* out);
 int ssw_cuda_device_count(void);
+/* Device memory is cached in a pool owned by this library between batches; this returns it to the driver. */
+int ssw_cuda_trim_pools(void);
 /* Measured issue rate of a dependency-free VIADDMNMX.S16x2 stream on `device`, in 32-bit
  * lane-instructions per second (the denominator of the DPX roofline). */
 int ssw_cuda_dpx_peak(int device, double* lane_instr_per_s, double* sm_clock_mhz);

@@ -93,3 +93,16 @@ def test_pack_pairs_and_scoring(sw):
     assert r_off.tolist() == [0, 0, 0] and r_len.tolist() == [4, 4, 4] and q_off.tolist() == [4, 5, 7]
     m = list(sw.make_scoring(10, 4, 8, 2).mat)
     assert m[0] == 10 and m[1] == -4 and m[4] == 0 and m[20:25] == [0] * 5
+
+
+def test_revcomp_matches_the_reference_table(sw):
+    """CIRI_long/utils.py:118-120 complements upper-case A/T/C/G only: lower-case (soft-masked genome) bases are
+    reversed but NOT complemented, N stays N.  The minus-strand windows of align_clip_segments_batch
+    (find_bsj.py:214) must be the same string the reference aligns against."""
+    from ciri_long_b200 import callsites as cs
+    ref_table = str.maketrans("ATCG", "TAGC")                   # the reference's own table, restated
+    for seq in ("ACGTN", "acgtn", "AAccGGttNn", "GATTACAgattacaNNNN", ""):
+        assert cs.revcomp(seq) == seq.translate(ref_table)[::-1]
+    assert cs.revcomp("AAccGG") == "CCccTT"                     # lower case reversed, not complemented
+    window = "ACGTacgtNNACGT"
+    assert cs.revcomp(window) == "ACGTNNtgcaACGT"

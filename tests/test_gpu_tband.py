@@ -138,3 +138,32 @@ def test_tband_default_threshold_and_repeat(sw, oracle):
         for i in range(0, len(b), 97):
             assert (c1[r1["cigar_off"][i]:r1["cigar_off"][i] + r1["cigar_len"][i]] ==
                     ca[ra["cigar_off"][i]:ra["cigar_off"][i] + ra["cigar_len"][i]]).all(), i
+
+
+@pytest.mark.parametrize("lane_kernel", [False, True])
+def test_band_escape_returns_coordinates_and_empty_cigar(sw, monkeypatch, lane_kernel):
+    """tests/golden/band_escape.json (score and coordinates from the unmodified reference): the traceback of these
+    pairs leaves the band, where the reference's CIGAR is undefined.  Both CIGAR instances, the legacy per-call
+    ABI and the Python wrapper return the exact coordinates with status 1 and an empty CIGAR."""
+    import json, os
+    GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    from ciri_long_b200 import workloads as W
+    monkeypatch.setenv("SSW_CUDA_TBAND_MIN", "0" if lane_kernel else "1000000000")
+    g = json.load(open(os.path.join(GOLDEN_DIR, "band_escape.json")))
+    for c in g["cases"]:
+        p, e = c["params"], c["expected"]
+        b = W.from_lists([O.encode(c["query"])], [O.encode(c["ref"])], tuple(p))
+        with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, *p, flag=1) as d:
+            d.run()
+            rec, cig = d.fetch()
+        r = rec[0]
+        assert (int(r["status"]) & 0xff) == 1 and int(r["cigar_len"]) == 0, (c["name"], int(r["status"]))
+        got = tuple(int(r[k]) for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2"))
+        assert got == tuple(e[k] for k in O.FIELDS), (c["name"], got)
+        al = sw.Aligner(c["ref"], p[0], p[1], p[2], p[3], report_secondary=True, report_cigar=True)
+        res = al.align(c["query"])
+        assert res is not None and res.cigar_string is None
+        assert (res.score, res.ref_begin, res.ref_end, res.query_begin, res.query_end) == \
+            (e["score"], e["ref_begin"], e["ref_end"], e["read_begin"], e["read_end"])
+        res2 = sw.align_pairs([c["ref"]], [c["query"]], *p, report_cigar=True)[0]
+        assert res2 is not None and res2.cigar_string is None and res2.ref_begin == e["ref_begin"]

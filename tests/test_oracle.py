@@ -112,3 +112,19 @@ def test_edit_distance_oracle_known_answers_and_properties():
             assert abs(len(a) - len(b)) <= d <= max(len(a), len(b))
     a, b, c = seqs[1], seqs[2], seqs[3]
     assert O.edit_distance(a, c) <= O.edit_distance(a, b) + O.edit_distance(b, c)
+
+
+def test_band_escape_goldens_are_reported_by_the_restatement(oracle):
+    """tests/golden/band_escape.json: pairs whose traceback leaves the band.  The reference's CIGAR is undefined
+    there (it reads direction bytes it never wrote, ssw.c:642-673); the restatement reports the outcome, and its
+    score / coordinates equal the reference's own (recorded with flag=4, filterd=-1)."""
+    import json, os
+    GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = json.load(open(os.path.join(GOLDEN_DIR, "band_escape.json")))
+    assert len(g["cases"]) >= 3
+    for c in g["cases"]:
+        q, r, p = O.encode(c["query"]), O.encode(c["ref"]), c["params"]
+        assert oracle.align(q, r, O.make_mat(p[0], p[1]), p[2], p[3], flag=1) is None
+        e = oracle.align(q, r, O.make_mat(p[0], p[1]), p[2], p[3], flag=0)
+        assert (e["score"], e["ref_end"], e["read_end"], e["score2"], e["ref_end2"]) == \
+            tuple(c["expected"][k] for k in ("score", "ref_end", "read_end", "score2", "ref_end2"))
