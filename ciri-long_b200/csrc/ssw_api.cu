@@ -12,7 +12,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -675,7 +677,10 @@ static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
     return SSW_OK;
 }
 
-extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used)
+// Results of a batch.  `reserve(used, &base)` names the destination of the batch's `used` CIGAR ops and the offset
+// that destination has in the caller's buffer (added to every cigar_off); NULL = it does not fit.
+template <typename Reserve>
+static int fetch_core(ssw_batch* b, ssw_result* out, Reserve reserve, int64_t* cigar_used)
 {
     if (!b || (!out && b->n > 0)) return SSW_ERR_ARG;
     CU_TRY(cudaSetDevice(b->device));
@@ -695,6 +700,7 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
         if (!big.empty()) { const int rc = rerun_big_bands(b, big); if (rc != SSW_OK) return rc; }
     }
     unsigned long long used = 0;
+    int64_t cig_base = 0;
     if (cigar_stage) {
         CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
@@ -715,9 +721,10 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
         if (cigar_used) *cigar_used = (int64_t)used;
         if ((long long)used > b->cigar_cap) { set_error("internal cigar buffer exhausted"); return SSW_ERR_CIGAR_CAP; }
         if (used > 0) {
-            if (!cigar_buf || (int64_t)used > cigar_cap) { set_error("cigar buffer too small"); return SSW_ERR_CIGAR_CAP; }
+            uint32_t* dst = reserve((int64_t)used, &cig_base);
+            if (!dst) { set_error("cigar buffer too small"); return SSW_ERR_CIGAR_CAP; }
             TraceTimer t2("  fetch: d2h cigars");
-            CU_TRY(cudaMemcpyAsync(cigar_buf, b->d_cigar, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(dst, b->d_cigar, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
         }
     }
@@ -727,13 +734,21 @@ extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_bu
         o.score1 = r.score1; o.score2 = r.score2;
         o.ref_begin1 = r.ref_begin1; o.ref_end1 = r.ref_end1;
         o.read_begin1 = r.read_begin1; o.read_end1 = r.read_end1; o.ref_end2 = r.ref_end2;
-        o.cigar_len = r.cigar_len; o.cigar_off = r.cigar_off; o.word = r.word;
+        o.cigar_len = r.cigar_len; o.cigar_off = r.cigar_off + cig_base; o.word = r.word;
         if (r.status & (PS_PUNT | PS_UNSUPPORTED | PS_NEED_GOTOH | PS_BAND_SCRATCH | PS_CIGAR_CAP)) o.status = SSW_PAIR_UNSUPPORTED;
         else if (r.status & PS_TRACEBACK_ERR) o.status = SSW_PAIR_TRACEBACK_ERR;
         else o.status = SSW_PAIR_OK;
         o.status |= r.status << 8;          // internal stage bits, for diagnostics (see ssw_cuda.h)
     }
     return SSW_OK;
+}
+
+extern "C" int ssw_batch_fetch(ssw_batch* b, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used)
+{
+    return fetch_core(b, out, [&](int64_t used, int64_t* base) -> uint32_t* {
+        *base = 0;
+        return (cigar_buf && used <= cigar_cap) ? cigar_buf : nullptr;
+    }, cigar_used);
 }
 
 static int error_code_of_create()
@@ -743,60 +758,114 @@ static int error_code_of_create()
          : (g_last_error.find("cuda") != std::string::npos ? SSW_ERR_CUDA : SSW_ERR_ARG));
 }
 
-// One-shot call on host buffers.  Large batches are cut into chunks of SSW_CUDA_CHUNK pairs (default
-// 262144: the lane-per-pair CIGAR instance wants batches that fill the machine several times over) that run as
-// separate device batches on alternating streams: the host-to-device copy of chunk
-// k+1 and the device-to-host copy of chunk k-1 overlap the kernels of chunk k (with pinned caller memory;
-// pageable memory still works, the copies then serialise).  Each chunk uploads only the byte range of
-// `seqs` its pairs reference, so a pair-major layout moves every byte once.
+// One-shot call on host buffers, on one or several devices of the box (pairs are
+// independent, so the batch shards with no exchange step and no collective).
+//
+// The pair list is cut into contiguous chunks of SSW_CUDA_CHUNK pairs (default 262144, fewer when that would
+// leave a device with less than ~8 chunks); one host thread per device pulls chunks from a shared counter --
+// longest-queue-first balancing without a cost model -- and runs each as its own device batch on alternating
+// streams: the host-to-device copy of chunk k+1 and the device-to-host copy of chunk k-1 overlap the kernels of
+// chunk k (with pinned caller memory; pageable memory still works, the copies then serialise).  A chunk uploads
+// only the byte range of `seqs` its pairs reference, so a pair-major layout moves every byte once and to one
+// device only.  Results land at the pairs' own indices (the host-side gather is the addressing); CIGAR space
+// in the caller's buffer is reserved with one atomic add per chunk, so cigar_off values are absolute.
+struct MultiJob {
+    int32_t n_pairs, chunk;
+    const int8_t* seqs; int64_t seqs_len;
+    const int64_t* q_off; const int32_t* q_len; const int64_t* r_off; const int32_t* r_len; const int32_t* mask_len;
+    const ssw_scoring* scoring;
+    ssw_result* out; uint32_t* cigar_buf; int64_t cigar_cap;
+    std::atomic<int64_t> next_chunk{0};
+    std::atomic<int64_t> cig_cursor{0};
+    std::atomic<int> rc{SSW_OK};
+    std::mutex err_mu; std::string err;
+    void fail(int code, const std::string& msg) { int ok = SSW_OK; if (rc.compare_exchange_strong(ok, code)) { std::lock_guard<std::mutex> g(err_mu); err = msg; } }
+};
+
+static void multi_worker(MultiJob* J, int device, int slots)
+{
+    constexpr int MAX_SLOTS = 4;
+    ssw_batch* slot[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t slot_p0[MAX_SLOTS] = {0, 0, 0, 0};
+    auto finish = [&](int sidx) {
+        ssw_batch* b = slot[sidx];
+        if (!b) return;
+        if (J->rc.load() == SSW_OK) {
+            int64_t used = 0;
+            const int r = fetch_core(b, J->out + slot_p0[sidx], [&](int64_t n, int64_t* base) -> uint32_t* {
+                const int64_t at = J->cig_cursor.fetch_add(n);
+                *base = at;
+                return (J->cigar_buf && at + n <= J->cigar_cap) ? J->cigar_buf + at : nullptr;
+            }, &used);
+            if (r != SSW_OK) J->fail(r, g_last_error);
+        }
+        ssw_batch_destroy(b);
+        slot[sidx] = nullptr;
+    };
+    const int64_t n_chunks = ((int64_t)J->n_pairs + J->chunk - 1) / J->chunk;
+    int k = 0;
+    for (;; ++k) {
+        if (J->rc.load() != SSW_OK) break;
+        const int64_t c = J->next_chunk.fetch_add(1);
+        if (c >= n_chunks) break;
+        const int32_t p0 = (int32_t)(c * J->chunk);
+        const int32_t cnt = std::min<int32_t>(J->chunk, J->n_pairs - p0);
+        const int sidx = k % slots;
+        finish(sidx);                                   // (normally already drained below)
+        ssw_batch* b = ssw_batch_create(device, nullptr, cnt, J->seqs, J->seqs_len, J->q_off + p0, J->q_len + p0, J->r_off + p0,
+                                        J->r_len + p0, J->mask_len ? J->mask_len + p0 : nullptr, J->scoring);
+        if (!b) { J->fail(error_code_of_create(), g_last_error); break; }
+        slot[sidx] = b; slot_p0[sidx] = p0;
+        const int r = ssw_batch_run(b);
+        if (r != SSW_OK) { J->fail(r, g_last_error); break; }
+        finish((k + 1) % slots);                        // the oldest chunk in flight on this device
+    }
+    for (int j = 1; j <= slots; ++j) finish((k + j) % slots);      // drain, oldest first
+    for (int sidx = 0; sidx < MAX_SLOTS; ++sidx) finish(sidx);
+}
+
+extern "C" int ssw_align_batch_multi(const int* devices, int n_devices, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                                     const int64_t* q_off, const int32_t* q_len, const int64_t* r_off, const int32_t* r_len,
+                                     const int32_t* mask_len, const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf,
+                                     int64_t cigar_cap, int64_t* cigar_used)
+{
+    if (cigar_used) *cigar_used = 0;
+    if (n_pairs <= 0) return n_pairs == 0 ? SSW_OK : SSW_ERR_ARG;
+    if (!devices || n_devices <= 0 || n_devices > 64) { set_error("ssw_align_batch_multi: invalid device list"); return SSW_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no usable CUDA device (libssw_cuda has no CPU path)"); return SSW_ERR_NODEVICE; }
+    for (int d = 0; d < n_devices; ++d)
+        if (devices[d] < 0 || devices[d] >= ndev) { set_error("ssw_align_batch_multi: device " + std::to_string(devices[d]) + " does not exist"); return SSW_ERR_NODEVICE; }
+    int32_t chunk = 262144;
+    if (const char* e = getenv("SSW_CUDA_CHUNK")) { const long v = atol(e); if (v > 0 && v < (1L << 30)) chunk = (int32_t)v; }
+    else if (n_devices > 1) {
+        // enough chunks per device for the shared queue to balance, not so small that a chunk stops filling a GPU
+        const int64_t want = (int64_t)n_pairs / ((int64_t)n_devices * 8);
+        chunk = (int32_t)std::max<int64_t>(65536, std::min<int64_t>(chunk, want));
+    }
+    int slots = 4;
+    if (const char* e = getenv("SSW_CUDA_SLOTS")) { const long v = atol(e); if (v >= 2 && v <= 4) slots = (int)v; }
+    MultiJob J;
+    J.n_pairs = n_pairs; J.chunk = chunk; J.seqs = seqs; J.seqs_len = seqs_len; J.q_off = q_off; J.q_len = q_len;
+    J.r_off = r_off; J.r_len = r_len; J.mask_len = mask_len; J.scoring = scoring; J.out = out; J.cigar_buf = cigar_buf; J.cigar_cap = cigar_cap;
+    if (n_devices == 1) multi_worker(&J, devices[0], slots);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n_devices; ++d) th.emplace_back(multi_worker, &J, devices[d], slots);
+        for (auto& t : th) t.join();
+    }
+    if (cigar_used) *cigar_used = J.cig_cursor.load();
+    if (J.rc.load() != SSW_OK) { set_error(J.err); return J.rc.load(); }
+    return SSW_OK;
+}
+
 extern "C" int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len, const int64_t* q_off,
                                const int32_t* q_len, const int64_t* r_off, const int32_t* r_len, const int32_t* mask_len,
                                const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap,
                                int64_t* cigar_used)
 {
-    int32_t chunk = 262144;
-    if (const char* e = getenv("SSW_CUDA_CHUNK")) { const long v = atol(e); if (v > 0 && v < (1L << 30)) chunk = (int32_t)v; }
-    if (cigar_used) *cigar_used = 0;
-    if (n_pairs <= 0) return n_pairs == 0 ? SSW_OK : SSW_ERR_ARG;
-    // chunks in flight: while the host waits for the oldest one, the kernels of the younger ones keep the
-    // SMs busy through each other's launch tails and their uploads overlap
-    constexpr int MAX_SLOTS = 4;
-    int slots = 4;
-    if (const char* e = getenv("SSW_CUDA_SLOTS")) { const long v = atol(e); if (v >= 2 && v <= MAX_SLOTS) slots = (int)v; }
-    ssw_batch* slot[MAX_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-    int32_t slot_p0[MAX_SLOTS] = {0, 0, 0, 0};
-    int64_t cig_base = 0;
-    int rc = SSW_OK;
-    auto finish = [&](int sidx) -> int {
-        ssw_batch* b = slot[sidx];
-        if (!b) return SSW_OK;
-        int64_t used = 0;
-        int r = ssw_batch_fetch(b, out + slot_p0[sidx], cigar_buf ? cigar_buf + cig_base : nullptr,
-                                cigar_buf ? cigar_cap - cig_base : 0, &used);
-        if (r == SSW_OK) {
-            for (int32_t p = 0; p < b->n; ++p) out[slot_p0[sidx] + p].cigar_off += cig_base;
-            cig_base += used;
-        } else if (r == SSW_ERR_CIGAR_CAP && cigar_used) *cigar_used = cig_base + used;
-        ssw_batch_destroy(b);
-        slot[sidx] = nullptr;
-        return r;
-    };
-    int k = 0;
-    for (int32_t p0 = 0; p0 < n_pairs && rc == SSW_OK; p0 += chunk, ++k) {
-        const int32_t cnt = std::min<int32_t>(chunk, n_pairs - p0);
-        const int sidx = k % slots;
-        ssw_batch* b = ssw_batch_create(device, nullptr, cnt, seqs, seqs_len, q_off + p0, q_len + p0, r_off + p0, r_len + p0,
-                                        mask_len ? mask_len + p0 : nullptr, scoring);
-        if (!b) { rc = error_code_of_create(); break; }
-        slot[sidx] = b; slot_p0[sidx] = p0;
-        rc = ssw_batch_run(b);
-        if (rc != SSW_OK) break;
-        rc = finish((k + 1) % slots);               // the oldest chunk in flight (results stay in pair order)
-    }
-    for (int j = 1; j <= slots && rc == SSW_OK; ++j) rc = finish((k + j) % slots);      // drain, oldest first
-    for (int sidx = 0; sidx < MAX_SLOTS; ++sidx) if (slot[sidx]) { ssw_batch_destroy(slot[sidx]); slot[sidx] = nullptr; }
-    if (rc == SSW_OK && cigar_used) *cigar_used = cig_base;
-    return rc;
+    return ssw_align_batch_multi(&device, 1, n_pairs, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len, scoring, out,
+                                 cigar_buf, cigar_cap, cigar_used);
 }
 
 extern "C" void ssw_encode_dna(const char* ascii, int64_t len, int8_t* codes)
@@ -985,7 +1054,9 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
     ssw_result res;
     std::vector<uint32_t> cig(2 * (size_t)prof->readLen + 16);
     int64_t used = 0;
-    const int rc = ssw_align_batch(0, 1, seqs.data(), (int64_t)seqs.size(), &q_off, &q_len, &r_off, &r_len, &mask, &sc,
+    int legacy_dev = 0;                                   // SSW_CUDA_DEVICE: which GPU serves the per-call ABI in this process
+    if (const char* e = getenv("SSW_CUDA_DEVICE")) legacy_dev = atoi(e);
+    const int rc = ssw_align_batch(legacy_dev, 1, seqs.data(), (int64_t)seqs.size(), &q_off, &q_len, &r_off, &r_len, &mask, &sc,
                                    &res, cig.data(), (int64_t)cig.size(), &used);
     if (rc != SSW_OK) {
         fprintf(stderr, "libssw_cuda: %s\n", g_last_error.c_str());

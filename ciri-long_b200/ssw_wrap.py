@@ -108,6 +108,10 @@ def _load():
     lib.ssw_align_batch.restype = c_int
     lib.ssw_align_batch.argtypes = [c_int, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     POINTER(SSWScoring), c_void_p, c_void_p, c_int64, POINTER(c_int64)]
+    lib.ssw_align_batch_multi.restype = c_int
+    lib.ssw_align_batch_multi.argtypes = [c_void_p, c_int, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, POINTER(SSWScoring), c_void_p, c_void_p, c_int64, POINTER(c_int64)]
+    lib.ssw_cuda_trim_pools.restype = c_int
     lib.ssw_cuda_last_error.restype = c_char_p
     lib.ssw_cuda_device_count.restype = c_int
     lib.ssw_cuda_dpx_peak.restype = c_int
@@ -501,9 +505,11 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
 
 
 def align_arrays(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend, flag=1, mask_len=None,
-                 device=0, out=None, cig=None):
-    """The one-shot C call (ssw_align_batch) on struct-of-arrays host buffers: upload, all kernels and
-    download in one call, chunk-pipelined inside the library.  Returns (records, cigar ops)."""
+                 device=0, out=None, cig=None, devices=None, filters=0, filterd=0):
+    """The one-shot C call (ssw_align_batch / ssw_align_batch_multi) on struct-of-arrays host buffers: upload, all
+    kernels and download in one call, chunk-pipelined inside the library.  ``devices=[0, 1, ...]`` spreads the
+    chunks over several GPUs of the box (one host thread per device, results gathered at the pairs' indices;
+    bit-identical to the single-device call).  Returns (records, cigar ops)."""
     seqs = np.ascontiguousarray(seqs, dtype=np.int8)
     q_off = np.ascontiguousarray(q_off, dtype=np.int64); r_off = np.ascontiguousarray(r_off, dtype=np.int64)
     q_len = np.ascontiguousarray(q_len, dtype=np.int32); r_len = np.ascontiguousarray(r_len, dtype=np.int32)
@@ -512,14 +518,16 @@ def align_arrays(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, ga
         out = np.zeros(n, dtype=RESULT_DTYPE)
     if cig is None:
         cig = np.empty(int(2 * q_len.astype(np.int64).sum() + 3 * n + 16) if flag else 1, dtype=np.uint32)
-    sc = make_scoring(match, mismatch, gap_open, gap_extend, flag)
+    sc = make_scoring(match, mismatch, gap_open, gap_extend, flag, filters, filterd)
     used = c_int64(0)
     ml = None if mask_len is None else np.ascontiguousarray(mask_len, dtype=np.int32)
-    rc = Aligner.libssw.ssw_align_batch(device, n, seqs.ctypes.data, seqs.size, q_off.ctypes.data, q_len.ctypes.data,
-                                        r_off.ctypes.data, r_len.ctypes.data, None if ml is None else ml.ctypes.data,
-                                        byref(sc), out.ctypes.data, cig.ctypes.data, len(cig), byref(used))
+    devs = np.ascontiguousarray([device] if devices is None else list(devices), dtype=np.int32)
+    rc = Aligner.libssw.ssw_align_batch_multi(devs.ctypes.data, len(devs), n, seqs.ctypes.data, seqs.size, q_off.ctypes.data,
+                                              q_len.ctypes.data, r_off.ctypes.data, r_len.ctypes.data,
+                                              None if ml is None else ml.ctypes.data, byref(sc), out.ctypes.data,
+                                              cig.ctypes.data, len(cig), byref(used))
     if rc != 0:
-        raise SSWCudaError("ssw_align_batch: %d %s" % (rc, Aligner.libssw.ssw_cuda_last_error().decode()))
+        raise SSWCudaError("ssw_align_batch_multi: %d %s" % (rc, Aligner.libssw.ssw_cuda_last_error().decode()))
     return out, cig[:used.value]
 
 

@@ -285,3 +285,189 @@ def long_query_short_ref_pairs(n_pairs, seed=SEED_BASE + 7, q_min=200, q_max=500
     r_codes, r_len = noisy_channel(q[src], np.full(n_pairs, ref_len, dtype=np.int64), rng)
     seqs, q_off2, r_off = _pack(q, ql.astype(np.int32), r_codes, r_len)
     return PairBatch(seqs, q_off2, ql.astype(np.int32), r_off, r_len, *params, name="S4S6-long-query")
+
+
+# ---- generators on the GPU (torch): the same recipes as above, a different random stream; a million pairs take
+# ---- seconds instead of minutes.  All return host (numpy) PairBatches.
+def _t_ragged_arange(starts, lens):
+    import torch
+    lens = lens.long()
+    total = int(lens.sum())
+    seg_start = torch.cumsum(lens, 0) - lens
+    return torch.repeat_interleave(starts.long() - seg_start, lens) + torch.arange(total, device=lens.device)
+
+
+def noisy_channel_torch(codes, seg_len, g, sub=0.05, ins=0.04, dele=0.04, max_run=3, n_frac=0.0):
+    """noisy_channel on the device: (codes int8 tensor, seg_len long tensor) -> (codes, seg_len)."""
+    import torch
+    dev = codes.device
+    total = codes.numel()
+    seg_id = torch.repeat_interleave(torch.arange(len(seg_len), device=dev), seg_len.long())
+    u = torch.rand(total, device=dev, generator=g)
+    keep = u >= dele
+    is_sub = keep & (u < dele + sub)
+    shift = torch.randint(1, 4, (total,), dtype=torch.int8, device=dev, generator=g)
+    codes = torch.where(is_sub, (codes + shift) % 4, codes)
+    runs = torch.where(torch.rand(total, device=dev, generator=g) < ins,
+                       torch.randint(1, max_run + 1, (total,), device=dev, generator=g),
+                       torch.zeros((), dtype=torch.long, device=dev))
+    reps = keep.long() + runs
+    new = torch.repeat_interleave(codes, reps)
+    grp_start = torch.cumsum(reps, 0) - reps
+    pos = torch.arange(new.numel(), device=dev) - torch.repeat_interleave(grp_start, reps)
+    inserted = pos >= torch.repeat_interleave(keep.long(), reps)
+    rnd = torch.randint(0, 4, (new.numel(),), dtype=torch.int8, device=dev, generator=g)
+    new = torch.where(inserted, rnd, new)
+    if n_frac > 0:
+        new = torch.where(torch.rand(new.numel(), device=dev, generator=g) < n_frac,
+                          torch.full((), 4, dtype=torch.int8, device=dev), new)
+    new_len = torch.bincount(torch.repeat_interleave(seg_id, reps), minlength=len(seg_len))
+    return new, new_len
+
+
+def _pack_torch(q_codes, q_len, r_codes, r_len):
+    """[q0 r0 q1 r1 ...] in one buffer, on the device; returns host arrays (seqs, q_off, r_off)."""
+    import torch
+    n = len(q_len)
+    lens = torch.stack([q_len.long(), r_len.long()], 1).reshape(-1)
+    offs = torch.cumsum(lens, 0) - lens
+    q_off, r_off = offs[0::2], offs[1::2]
+    seqs = torch.empty(int(lens.sum()), dtype=torch.int8, device=q_codes.device)
+    seqs[_t_ragged_arange(q_off, q_len)] = q_codes
+    seqs[_t_ragged_arange(r_off, r_len)] = r_codes
+    return seqs.cpu().numpy(), q_off.cpu().numpy().astype(np.int64), r_off.cpu().numpy().astype(np.int64)
+
+
+def square_pairs_torch(n_pairs, length, device, seed=SEED_BASE + 4, params=(1, 1, 1, 1)):
+    """Config C4 on the device: m ~ n ~ length."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed + length)
+    refs = torch.randint(0, 4, (n_pairs * length,), dtype=torch.int8, device=device, generator=g)
+    ql0 = torch.full((n_pairs,), length, dtype=torch.long, device=device)
+    q, ql = noisy_channel_torch(refs, ql0, g)
+    seqs, q_off, r_off = _pack_torch(q, ql, refs, ql0)
+    return PairBatch(seqs, q_off, ql.cpu().numpy().astype(np.int32), r_off, np.full(n_pairs, length, dtype=np.int32), *params,
+                     name="C4-square-%d" % length)
+
+
+def rolling_circle_pairs_torch(n_reads, device, seed=SEED_BASE + 3, read_min=2000, read_max=6000, copies_min=2, copies_max=8,
+                               params=(10, 4, 8, 2), chunk=20000):
+    """Config C3 on the device (rolling_circle_pairs recipe), generated in chunks of reads."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    parts = []
+    for c0 in range(0, n_reads, chunk):
+        n = min(chunk, n_reads - c0)
+        read_len = torch.randint(read_min, read_max + 1, (n,), device=device, generator=g)
+        copies = torch.randint(copies_min, copies_max + 1, (n,), device=device, generator=g)
+        unit_len = torch.clamp(read_len // copies, min=20)
+        seg_unit = torch.repeat_interleave(torch.arange(n, device=device), copies)
+        seg_len0 = unit_len[seg_unit]
+        unit_off = torch.cumsum(unit_len, 0) - unit_len
+        units = torch.randint(0, 4, (int(unit_len.sum()),), dtype=torch.int8, device=device, generator=g)
+        rot = (torch.rand(n, device=device, generator=g) * unit_len.float()).long()
+        idx_in = _t_ragged_arange(torch.zeros(len(seg_len0), dtype=torch.long, device=device), seg_len0)
+        seg_rep = torch.repeat_interleave(torch.arange(len(seg_len0), device=device), seg_len0)
+        su = seg_unit[seg_rep]
+        src = unit_off[su] + (idx_in + rot[su]) % unit_len[su]
+        seg_codes, seg_len = noisy_channel_torch(units[src], seg_len0, g)
+        seg_off = torch.cumsum(seg_len, 0) - seg_len
+        first_seg = torch.cumsum(copies, 0) - copies
+        is_query = torch.ones(len(seg_len), dtype=torch.bool, device=device)
+        is_query[first_seg] = False
+        q_idx = torch.nonzero(is_query).squeeze(1)
+        r_idx = first_seg[seg_unit[q_idx]]
+        ok = (seg_len[q_idx] > 0) & (seg_len[r_idx] > 0)
+        q_idx, r_idx = q_idx[ok], r_idx[ok]
+        parts.append(PairBatch(seg_codes.cpu().numpy(), seg_off[q_idx].cpu().numpy().astype(np.int64),
+                               seg_len[q_idx].cpu().numpy().astype(np.int32), seg_off[r_idx].cpu().numpy().astype(np.int64),
+                               seg_len[r_idx].cpu().numpy().astype(np.int32), *params, name="C3-rolling-circle"))
+    return concat_batches(parts, name="C3-rolling-circle") if len(parts) > 1 else parts[0]
+
+
+def junction_pairs_torch(n_pairs, device, seed=SEED_BASE + 5, q_min=40, q_max=60, ref_len=20, params=(10, 4, 8, 2)):
+    """S2-like tiny pairs on the device (junction_pairs recipe)."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    ql = torch.randint(q_min, q_max + 1, (n_pairs,), device=device, generator=g)
+    q = torch.randint(0, 4, (int(ql.sum()),), dtype=torch.int8, device=device, generator=g)
+    q_off = torch.cumsum(ql, 0) - ql
+    st = (torch.rand(n_pairs, device=device, generator=g) * (ql - ref_len + 1).float()).long()
+    rl0 = torch.full((n_pairs,), ref_len, dtype=torch.long, device=device)
+    src = _t_ragged_arange(q_off + st, rl0)
+    r_codes, r_len = noisy_channel_torch(q[src], rl0, g)
+    seqs, q_off2, r_off = _pack_torch(q, ql, r_codes, r_len)
+    return PairBatch(seqs, q_off2, ql.cpu().numpy().astype(np.int32), r_off, r_len.cpu().numpy().astype(np.int32), *params,
+                     name="S2-junction")
+
+
+def long_query_short_ref_pairs_torch(n_pairs, device, seed=SEED_BASE + 7, q_min=200, q_max=5000, ref_len=50, params=(10, 4, 8, 2)):
+    """S4/S6-like pairs on the device (long_query_short_ref_pairs recipe)."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    ql = torch.randint(q_min, q_max + 1, (n_pairs,), device=device, generator=g)
+    q = torch.randint(0, 4, (int(ql.sum()),), dtype=torch.int8, device=device, generator=g)
+    q_off = torch.cumsum(ql, 0) - ql
+    st = (torch.rand(n_pairs, device=device, generator=g) * (ql - ref_len + 1).float()).long()
+    rl0 = torch.full((n_pairs,), ref_len, dtype=torch.long, device=device)
+    src = _t_ragged_arange(q_off + st, rl0)
+    r_codes, r_len = noisy_channel_torch(q[src], rl0, g)
+    seqs, q_off2, r_off = _pack_torch(q, ql, r_codes, r_len)
+    return PairBatch(seqs, q_off2, ql.cpu().numpy().astype(np.int32), r_off, r_len.cpu().numpy().astype(np.int32), *params,
+                     name="S4S6-long-query")
+
+
+def clip_window_pairs_torch(n_pairs, device, seed=SEED_BASE + 8, q_min=20, q_max=600, win_min=400000, win_max=600000,
+                            genome_len=1 << 26, params=(1, 1, 1, 1)):
+    """S1 (find_bsj.py:191-215): the clipped bases of a read (20-600 nt) against the +-200 kb genomic window around
+    its hit.  Windows are views into one synthetic genome (offsets are explicit in the C ABI, so the windows of
+    neighbouring reads overlap in memory exactly like the reference's `env.GENOME.seq(ctg, st, en)` slices of one
+    chromosome); the clip is a noisy copy of a stretch inside its window."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    genome = torch.randint(0, 4, (genome_len,), dtype=torch.int8, device=device, generator=g)
+    wl = torch.randint(win_min, win_max + 1, (n_pairs,), device=device, generator=g)
+    ws = (torch.rand(n_pairs, device=device, generator=g, dtype=torch.float64) * (genome_len - wl).double()).long()
+    ql0 = torch.randint(q_min, q_max + 1, (n_pairs,), device=device, generator=g)
+    qs = ws + (torch.rand(n_pairs, device=device, generator=g, dtype=torch.float64) * (wl - ql0).double()).long()
+    src = _t_ragged_arange(qs, ql0)
+    q, ql = noisy_channel_torch(genome[src], ql0, g, n_frac=0.005)
+    ql = torch.clamp(ql, min=1)
+    q_off = genome_len + torch.cumsum(ql, 0) - ql
+    seqs = torch.cat([genome, q[:int(ql.sum())]]).cpu().numpy()
+    return PairBatch(seqs, q_off.cpu().numpy().astype(np.int64), ql.cpu().numpy().astype(np.int32), ws.cpu().numpy().astype(np.int64),
+                     wl.cpu().numpy().astype(np.int32), *params, name="S1-clip-vs-window")
+
+
+def repack(batch, order=None):
+    """Rebuild the code buffer in pair order [q0 r0 q1 r1 ...] (optionally after permuting the pairs), so that any
+    contiguous run of pairs references a compact byte range -- what the chunked one-shot call uploads."""
+    n = len(batch)
+    order = np.arange(n) if order is None else np.asarray(order)
+    ql, rl = batch.q_len[order], batch.r_len[order]
+    q_src = _ragged_arange(batch.q_off[order], ql)
+    r_src = _ragged_arange(batch.r_off[order], rl)
+    seqs, q_off, r_off = _pack(batch.seqs[q_src], ql, batch.seqs[r_src], rl)
+    return PairBatch(seqs, q_off, ql.copy(), r_off, rl.copy(), batch.match, batch.mismatch, batch.gap_open, batch.gap_extend,
+                     batch.name)
+
+
+def mixed_slab_torch(n_pairs, device, seed, params=(10, 4, 8, 2)):
+    """One slab of config C5: 60 % S2-like junction pairs (collapse.py:165-172), 25 % C2-like
+    segment-vs-flank pairs, 10 % C3-like rolling-circle segment pairs (collapse.py:259-265), 5 % S4/S6-like long
+    reads vs a 50-nt junction (collapse.py:373-387); one scoring scheme (collapse's 10/4/8/2), shuffled, repacked
+    pair-major."""
+    n2 = int(n_pairs * 0.60); nc2 = int(n_pairs * 0.25); n46 = int(n_pairs * 0.05)
+    nc3 = n_pairs - n2 - nc2 - n46
+    parts = [junction_pairs_torch(n2, device, seed=seed + 1, params=params),
+             bsj_refinement_pairs_torch(nc2, device, seed=seed + 2, params=params),
+             long_query_short_ref_pairs_torch(n46, device, seed=seed + 4, params=params)]
+    c3 = rolling_circle_pairs_torch(max(8, int(nc3 / 3.6)), device, seed=seed + 3, params=params)
+    if len(c3) >= nc3:
+        c3 = PairBatch(c3.seqs, c3.q_off[:nc3], c3.q_len[:nc3], c3.r_off[:nc3], c3.r_len[:nc3], *params, name=c3.name)
+    parts.append(c3)
+    mix = concat_batches(parts, name="C5-mixed")
+    order = np.random.default_rng(seed).permutation(len(mix))
+    out = repack(mix, order)
+    out.name = "C5-mixed"
+    return out

@@ -146,6 +146,17 @@ int ssw_align_batch(int device, int32_t n_pairs, const int8_t* seqs, int64_t seq
                     const int32_t* mask_len, const ssw_scoring* scoring,
                     ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
 
+/* The same call over several devices of one box (SURVEY.md section 7's `devices, n_devices` signature; section 8e:
+ * pairs are independent, no collective).  The pair list is cut into contiguous chunks that one host thread per
+ * device pulls from a shared queue; every chunk uploads only the bytes its pairs reference, results land at the
+ * pairs' own indices, cigar_off values are absolute offsets into cigar_buf.  Results are bit-identical to the
+ * single-device call.  ssw_align_batch(device, ...) is this call with one device. */
+int ssw_align_batch_multi(const int* devices, int n_devices, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                          const int64_t* q_off, const int32_t* q_len,
+                          const int64_t* r_off, const int32_t* r_len,
+                          const int32_t* mask_len, const ssw_scoring* scoring,
+                          ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
+
 /* ASCII -> {0..4} on the device-facing side of the boundary: vectorised replacement for the
  * per-base Python loop of ssw_wrap.py:234-252 (A C G T N, either case; anything else -> 4). */
 void ssw_encode_dna(const char* ascii, int64_t len, int8_t* codes);

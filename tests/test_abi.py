@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(sw):
     names = set(re.findall(r"\b(ssw_\w+|init_destroy|align_destroy|cigar_int_to_op|cigar_int_to_len)\s*\(", hdr))
     names -= {"ssw_scoring", "ssw_result", "ssw_batch"}
     assert {"ssw_init", "ssw_align", "init_destroy", "align_destroy", "cigar_int_to_op", "cigar_int_to_len",
-            "ssw_batch_create", "ssw_batch_run", "ssw_batch_fetch", "ssw_batch_destroy", "ssw_align_batch",
+            "ssw_batch_create", "ssw_batch_run", "ssw_batch_fetch", "ssw_batch_destroy", "ssw_align_batch", "ssw_align_batch_multi",
             "ssw_batch_stage_ms", "ssw_encode_dna", "ssw_cuda_dpx_peak"} <= names
     lib = ctypes.CDLL(os.path.join(ROOT, "ciri-long_b200", "libssw_cuda.so"))
     for n in sorted(names):
