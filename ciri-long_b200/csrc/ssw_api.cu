@@ -131,6 +131,7 @@ struct ssw_batch {
     unsigned long long* d_cigar_used = nullptr;
     // host-side shape summary
     int max_q = 0, max_r = 0, maxK = 0;
+    int max_rows = 0;                    // bound on the rows of any pair's trimmed rectangle (CIGAR scratch)
     bool have[2][2][KMAX + 1];           // forward lists known to be non-empty: [cls][kind][K]
     bool have_t2[2][KMAX + 1];           // GOTOH-first pairs that may overflow and move on to TRUNC: [cls][K]
     // long references (class 1): forward pass over column chunks (ssw_kernels.h: ChunkPlan)
@@ -252,6 +253,10 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
             b->maxK = std::max(b->maxK, std::max(K, strip_height_for(m, 0)));
             cig_worst += 2LL * m + 3;
             q_total += m;
+            // rows of the trimmed rectangle = aligned query span <= query length, and a local alignment cannot hold more
+            // inserted query bases than its matches pay for: span <= r * (1 + maxScore / gap_extend)
+            const long long span = std::min<long long>(m, (long long)r * (1 + (maxScore + b->sc.ge - 1) / std::max(1, (int)b->sc.ge)) + 1);
+            b->max_rows = std::max<int>(b->max_rows, (int)span);
         }
     }
     if (hi < lo) { lo = 0; hi = 0; }
@@ -331,9 +336,9 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->use_tband = n >= tband_min;
         long long blocks = 0;
         if (b->use_tband) {
-            long long budget = SCRATCH_BUDGET;
+            long long budget = 8LL << 30;                // direction words of the resident lock-step rounds (HBM: 180 GB)
             if (const char* e = getenv("SSW_CUDA_TBAND_BUDGET_MB")) { const long v = atol(e); if (v > 0) budget = (long long)v << 20; }
-            CU_TRY(tband_plan(b->device, b->sms, b->max_q, budget, &b->tplan));
+            CU_TRY(tband_plan(b->device, b->sms, b->max_rows, budget, &b->tplan));
             CU_TRY(tband_configure());
             CU_TRY(dev_alloc_t(&b->d_tscr, (size_t)b->tplan.scratch_bytes, st));
             CU_TRY(dev_alloc_t(&b->d_tlists, 4 * nn, st));

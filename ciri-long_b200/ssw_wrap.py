@@ -138,6 +138,18 @@ class SSWCudaError(RuntimeError):
     pass
 
 
+# Opt-in: route this process's alignments through a GPU-owner service (server.py) instead of the local library.
+# Meant for forked pool workers (find_bsj.py:338-345, collapse.py:842-851), which must not create CUDA contexts of
+# their own: ``Aligner.align`` then blocks on the service, so unmodified call sites batch across workers.
+_SERVICE = None
+
+
+def use_service(client):
+    """client: server.AlignClient (or None to go back to the in-process library)."""
+    global _SERVICE
+    _SERVICE = client
+
+
 #~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~#
 class DeviceBatch(object):
     """A batch of independent (query, reference) pairs resident in device memory (ssw_batch_*)."""
@@ -276,6 +288,7 @@ class Aligner(object):
         self.mat = make_scoring(match, mismatch, 0, 0).mat
 
     def set_ref(self, ref_seq):
+        self._ref_src = ref_seq
         if ref_seq is not None and len(ref_seq):
             self.ref_len = len(ref_seq)
             self.ref_seq = self._DNA_to_int_mat(ref_seq, self.ref_len)
@@ -287,6 +300,8 @@ class Aligner(object):
 
     def align(self, query_seq, min_score=0, min_len=0):
         """One pair through the legacy C ABI (ssw_init / ssw_align), same flow as ssw_wrap.py:174-230."""
+        if _SERVICE is not None:
+            return self._align_via_service(query_seq, min_score, min_len)
         query_len = len(query_seq)
         query_seq = self._DNA_to_int_mat(query_seq, query_len)
         profile = self.ssw_init(query_seq, c_int32(query_len), self.mat, 5, 2)
@@ -318,6 +333,17 @@ class Aligner(object):
                            device=device, _shared_ref=True)
 
     #~~~~~~~PRIVATE METHODS~~~~~~~#
+
+    def _align_via_service(self, query_seq, min_score, min_len):
+        """the same call, executed by the GPU-owner process (server.py); this process never touches the device"""
+        as_str = lambda x: x if isinstance(x, str) else "".join("ACGTN"[min(int(c) & 0xff, 4)] for c in x)
+        rec, cig = _SERVICE.align(as_str(self._ref_src), as_str(query_seq), self.match, self.mismatch, self.gap_open,
+                                  self.gap_extend, need_cigar=True)
+        if (rec['status'] & 0xff) not in (0, 1):
+            return None
+        if rec['score1'] >= min_score and rec['read_end1'] - rec['read_begin1'] + 1 >= min_len:
+            return PyAlignRes.from_record(rec, cig, len(query_seq), self.report_secondary, self.report_cigar)
+        return None
 
     def _DNA_to_int_mat(self, seq, len_seq):
         codes = encode_dna(seq)
@@ -479,6 +505,13 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
         is_ascii = False
     if need_cigar is None:
         need_cigar = report_cigar
+    if _SERVICE is not None and all(isinstance(x, str) for x in refs) and all(isinstance(x, str) for x in queries):
+        rec, cig = _SERVICE.align_pairs(refs, queries, match, mismatch, gap_open, gap_extend, need_cigar=need_cigar)
+        if as_records:
+            return rec, cig
+        q_len = [len(q) for q in queries]
+        return [None if (r['status'] & 0xff) not in (0, 1) or r['score1'] < min_score or r['read_end1'] - r['read_begin1'] + 1 < min_len
+                else PyAlignRes.from_record(r, cig, q_len[i], report_secondary, report_cigar) for i, r in enumerate(rec)]
     # flag 1 = begin + CIGAR (what the reference wrapper always asks for); flag 8 is not defined by the
     # reference -- the begin-only mode is expressed with the distance filter: bit 2 with filterd < 0
     flag = 1 if need_cigar else 4
