@@ -103,6 +103,8 @@ struct ssw_batch {
     long long seq_lo = 0, seq_hi = 0;
     std::vector<int32_t> h_mask;
     bool ascii_done = false;
+    bool packed = false;                 // the caller's sequence buffer holds two bases per byte (offsets count bases)
+    unsigned char* d_packed = nullptr;
     std::vector<int64_t> h_col_off;
     int8_t* d_seqs = nullptr;
     long long *d_qoff = nullptr, *d_roff = nullptr;
@@ -125,6 +127,8 @@ struct ssw_batch {
     bool no_cigar = false;                           // (flag & 4) with filterd < 0: no pair can pass the CIGAR gate (ssw.c:850)
     TbandPlan tplan;
     unsigned char* d_tscr = nullptr;
+    cudaStream_t tside[TBAND_INSTANCES + 1] = {};    // one stream per instance + one for the hand-overs
+    cudaEvent_t tev[TBAND_INSTANCES + 3] = {};
     int32_t *d_tlists = nullptr, *d_tbins = nullptr; // keys | sorted | list a | list b ;  bin_count | bin_base | seg | counts
     uint32_t* d_cigar = nullptr;
     long long cigar_cap = 0, cigar_worst = 0;
@@ -190,10 +194,12 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     dev_free(b->d_mask, fs); dev_free(b->d_rec, fs); dev_free(b->d_idx, fs); dev_free(b->d_idx2, fs); dev_free(b->d_idx3, fs); dev_free(b->d_idx4, fs); dev_free(b->d_meta, fs);
     dev_free(b->d_col_off, fs); dev_free(b->d_col_pool, fs); dev_free(b->d_pair_key, fs); dev_free(b->d_pair_left, fs);
     dev_free(b->d_task, fs); dev_free(b->d_task_meta, fs); dev_free(b->d_rtask, fs); dev_free(b->d_rres, fs);
-    dev_free(b->d_tscr, fs); dev_free(b->d_tlists, fs); dev_free(b->d_tbins, fs);
+    dev_free(b->d_packed, fs); dev_free(b->d_tscr, fs); dev_free(b->d_tlists, fs); dev_free(b->d_tbins, fs);
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+    for (auto& x : b->tside) if (x) cudaStreamDestroy(x);
+    for (auto& x : b->tev) if (x) cudaEventDestroy(x);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -260,12 +266,13 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         }
     }
     if (hi < lo) { lo = 0; hi = 0; }
+    if (b->packed) lo &= ~31LL;                          // packed upload: start on a byte (and 16-byte) boundary of the packed buffer
     b->seq_lo = lo; b->seq_hi = hi;
     // Allocation sizes are functions of these three numbers; they are rounded up so that consecutive
     // batches of similar shape request identical blocks and the stream-ordered pool can hand the same
     // memory back instead of growing.
     const int cap_q = (b->max_q + 255) & ~255, cap_r = (b->max_r + 255) & ~255;
-    const size_t cap_seq = ((size_t)(hi - lo) + (4u << 20)) & ~(size_t)((4u << 20) - 1);
+    const size_t cap_seq = ((size_t)(hi - lo) + 64 + (4u << 20)) & ~(size_t)((4u << 20) - 1);
     CU_TRY(cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, b->device));
 
     cudaStream_t st = b->stream;
@@ -284,7 +291,14 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     CU_TRY(cudaMemcpyAsync(b->d_mask, b->h_mask.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     // only the bytes the pairs of this batch reference travel; with pinned caller memory this copy is
     // asynchronous (the caller keeps `seqs` alive until ssw_batch_fetch, like every CUDA async copy)
-    if (hi > lo) CU_TRY(cudaMemcpyAsync(b->d_seqs, seqs + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+    if (hi > lo && !b->packed) CU_TRY(cudaMemcpyAsync(b->d_seqs, seqs + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+    if (hi > lo && b->packed) {
+        // half the bytes cross PCIe; the device expands them to one code per byte (what every kernel reads)
+        const long long nb = (hi - lo + 1) / 2;
+        CU_TRY(dev_alloc_t(&b->d_packed, (size_t)nb + 16, st));
+        CU_TRY(cudaMemcpyAsync(b->d_packed, reinterpret_cast<const unsigned char*>(seqs) + lo / 2, (size_t)nb, cudaMemcpyHostToDevice, st));
+        CU_TRY(unpack4(b->d_packed, b->d_seqs, nb, st));
+    }
 
     if (b->chunk_cols) {
         b->task_total = 0;
@@ -336,10 +350,12 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->use_tband = n >= tband_min;
         long long blocks = 0;
         if (b->use_tband) {
-            long long budget = 8LL << 30;                // direction words of the resident lock-step rounds (HBM: 180 GB)
+            long long budget = 16LL << 30;               // direction words of the resident lock-step rounds (HBM: 180 GB)
             if (const char* e = getenv("SSW_CUDA_TBAND_BUDGET_MB")) { const long v = atol(e); if (v > 0) budget = (long long)v << 20; }
             CU_TRY(tband_plan(b->device, b->sms, b->max_rows, budget, &b->tplan));
             CU_TRY(tband_configure());
+            for (auto& x : b->tside) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+            for (auto& x : b->tev) CU_TRY(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
             CU_TRY(dev_alloc_t(&b->d_tscr, (size_t)b->tplan.scratch_bytes, st));
             CU_TRY(dev_alloc_t(&b->d_tlists, 4 * nn, st));
             CU_TRY(dev_alloc_t(&b->d_tbins, 2 * (size_t)TBAND_BINS + 64, st));
@@ -356,7 +372,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->wdir = std::min<long long>(1024LL * rows + 65536, 64LL << 20);
         b->wstride = ((long long)b->bstage * 4 + b->wdir + 255) & ~255LL;
         blocks = std::min<long long>((long long)b->sms * 2, (n + BAND_WARPS - 1) / BAND_WARPS);
-        blocks = std::max<long long>(1, std::min<long long>(blocks, SCRATCH_BUDGET / (b->wstride * BAND_WARPS)));
+        blocks = std::max<long long>(1, std::min<long long>(blocks, (b->use_tband ? 8LL << 30 : SCRATCH_BUDGET) / (b->wstride * BAND_WARPS)));
         b->wblocks = (int)blocks;
         CU_TRY(dev_alloc_t(&b->d_wscr, (size_t)(blocks * BAND_WARPS * b->wstride), st));
         // CIGAR output: the worst case is 2*len(query)+3 ops per pair; real alignments need a small
@@ -368,9 +384,37 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     return SSW_OK;
 }
 
+static ssw_batch* batch_create_impl(int device, void* stream, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                                    const int64_t* q_off, const int32_t* q_len, const int64_t* r_off,
+                                    const int32_t* r_len, const int32_t* mask_len, const ssw_scoring* scoring, bool packed);
+
 extern "C" ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
                                        const int64_t* q_off, const int32_t* q_len, const int64_t* r_off,
                                        const int32_t* r_len, const int32_t* mask_len, const ssw_scoring* scoring)
+{
+    return batch_create_impl(device, stream, n_pairs, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len, scoring, false);
+}
+
+extern "C" ssw_batch* ssw_batch_create_packed(int device, void* stream, int32_t n_pairs, const uint8_t* packed, int64_t n_bases,
+                                              const int64_t* q_off, const int32_t* q_len, const int64_t* r_off,
+                                              const int32_t* r_len, const int32_t* mask_len, const ssw_scoring* scoring)
+{
+    return batch_create_impl(device, stream, n_pairs, reinterpret_cast<const int8_t*>(packed), n_bases, q_off, q_len, r_off, r_len,
+                             mask_len, scoring, true);
+}
+
+extern "C" void ssw_pack_dna4(const int8_t* codes, int64_t n, uint8_t* packed)
+{
+    for (int64_t k = 0; k + 1 < n; k += 2) {
+        const unsigned a = (unsigned char)codes[k] > 4 ? 4u : (unsigned char)codes[k], c = (unsigned char)codes[k + 1] > 4 ? 4u : (unsigned char)codes[k + 1];
+        packed[k >> 1] = (uint8_t)(a | (c << 4));
+    }
+    if (n & 1) packed[n >> 1] = (uint8_t)((unsigned char)codes[n - 1] > 4 ? 4 : codes[n - 1]);
+}
+
+static ssw_batch* batch_create_impl(int device, void* stream, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                                    const int64_t* q_off, const int32_t* q_len, const int64_t* r_off,
+                                    const int32_t* r_len, const int32_t* mask_len, const ssw_scoring* scoring, bool packed)
 {
     if (n_pairs < 0 || !scoring || (n_pairs > 0 && (!seqs || !q_off || !q_len || !r_off || !r_len))) {
         set_error("ssw_batch_create: invalid argument");
@@ -390,6 +434,7 @@ extern "C" ssw_batch* ssw_batch_create(int device, void* stream, int32_t n_pairs
     ssw_batch* b = new ssw_batch();
     b->device = device;
     b->n = n_pairs;
+    b->packed = packed;
     memcpy(b->sc.mat, scoring->mat, 25);
     b->sc.go = scoring->gap_open; b->sc.ge = scoring->gap_extend;
     int minv = 0;
@@ -444,7 +489,35 @@ static int enqueue_cigar_stage(ssw_batch* b, int* launches)
         ta.row_pairs_cap = b->tplan.row_pairs_cap; ta.stage_cap = b->tplan.stage_cap;
         ta.cigar_buf = b->d_cigar; ta.cigar_cap = b->cigar_cap; ta.cigar_used = b->d_cigar_used;
         int32_t* cnt = b->d_tbins + 2 * TBAND_BINS + 32;
-        CU_TRY(launch_tband(ta, b->tplan, ls.idx, ls.count, b->n, b->d_tlists + 2 * nn, b->d_tlists + 3 * nn, cnt, cnt + 1, st, launches));
+        // the warp-per-pair instances start on the first pass's hand-overs (wide bands, score-0 pairs, thin segments)
+        // on their own stream, next to the lane kernel; a second pair of launches after the last pass takes the rest
+        BandArgs early = ba;
+        early.scratch = b->d_wscr; early.scratch_stride = b->wstride; early.dir_bytes = b->wdir;
+        cudaStream_t fb = b->tside[TBAND_INSTANCES];
+        cudaEvent_t evFb = b->tev[TBAND_INSTANCES + 1];
+        const int wblocks = b->wblocks;
+        ssw_batch* bb = b;
+        auto after_first_sort = [=](cudaEvent_t sorted) -> cudaError_t {
+            cudaError_t e = cudaStreamWaitEvent(fb, sorted, 0);
+            if (e != cudaSuccess) return e;
+            // (the lists keep growing while these run: each launch works on a snapshot of its count, then the fetch
+            // cursor is put back on the snapshot for the closing launches)
+            BandArgs x = early;
+            int32_t* snap = cnt + 4;
+            if ((e = snapshot_count(snap, bb->count2(), fb)) != cudaSuccess) return e;
+            x.wl = WorkList{bb->d_idx2, nullptr, snap, bb->cursor2()};
+            if ((e = launch_band(1, x, wblocks, fb)) != cudaSuccess) return e;
+            if ((e = rewind_cursor(bb->cursor2(), snap, fb)) != cudaSuccess) return e;
+            if ((e = snapshot_count(snap + 1, bb->count3(), fb)) != cudaSuccess) return e;
+            x.wl = WorkList{bb->d_idx4, nullptr, snap + 1, bb->cursor3()};
+            if ((e = launch_band(2, x, wblocks, fb)) != cudaSuccess) return e;
+            if ((e = rewind_cursor(bb->cursor3(), snap + 1, fb)) != cudaSuccess) return e;
+            return cudaEventRecord(evFb, fb);
+        };
+        *launches += 2;
+        CU_TRY(launch_tband(ta, b->tplan, ls.idx, ls.count, b->n, b->d_tlists + 2 * nn, b->d_tlists + 3 * nn, cnt, cnt + 1, st,
+                            b->tside, b->tev, after_first_sort, launches));
+        CU_TRY(cudaStreamWaitEvent(st, evFb, 0));
     } else {
         CU_TRY(launch_band(0, ba, b->bblocks, st));
         *launches += 1;
@@ -779,6 +852,7 @@ struct MultiJob {
     const int8_t* seqs; int64_t seqs_len;
     const int64_t* q_off; const int32_t* q_len; const int64_t* r_off; const int32_t* r_len; const int32_t* mask_len;
     const ssw_scoring* scoring;
+    bool packed = false;
     ssw_result* out; uint32_t* cigar_buf; int64_t cigar_cap;
     std::atomic<int64_t> next_chunk{0};
     std::atomic<int64_t> cig_cursor{0};
@@ -817,8 +891,8 @@ static void multi_worker(MultiJob* J, int device, int slots)
         const int32_t cnt = std::min<int32_t>(J->chunk, J->n_pairs - p0);
         const int sidx = k % slots;
         finish(sidx);                                   // (normally already drained below)
-        ssw_batch* b = ssw_batch_create(device, nullptr, cnt, J->seqs, J->seqs_len, J->q_off + p0, J->q_len + p0, J->r_off + p0,
-                                        J->r_len + p0, J->mask_len ? J->mask_len + p0 : nullptr, J->scoring);
+        ssw_batch* b = batch_create_impl(device, nullptr, cnt, J->seqs, J->seqs_len, J->q_off + p0, J->q_len + p0, J->r_off + p0,
+                                         J->r_len + p0, J->mask_len ? J->mask_len + p0 : nullptr, J->scoring, J->packed);
         if (!b) { J->fail(error_code_of_create(), g_last_error); break; }
         slot[sidx] = b; slot_p0[sidx] = p0;
         const int r = ssw_batch_run(b);
@@ -829,10 +903,33 @@ static void multi_worker(MultiJob* J, int device, int slots)
     for (int sidx = 0; sidx < MAX_SLOTS; ++sidx) finish(sidx);
 }
 
+static int align_multi_impl(const int* devices, int n_devices, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                            const int64_t* q_off, const int32_t* q_len, const int64_t* r_off, const int32_t* r_len,
+                            const int32_t* mask_len, const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf,
+                            int64_t cigar_cap, int64_t* cigar_used, bool packed);
+
 extern "C" int ssw_align_batch_multi(const int* devices, int n_devices, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
                                      const int64_t* q_off, const int32_t* q_len, const int64_t* r_off, const int32_t* r_len,
                                      const int32_t* mask_len, const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf,
                                      int64_t cigar_cap, int64_t* cigar_used)
+{
+    return align_multi_impl(devices, n_devices, n_pairs, seqs, seqs_len, q_off, q_len, r_off, r_len, mask_len, scoring, out, cigar_buf,
+                            cigar_cap, cigar_used, false);
+}
+
+extern "C" int ssw_align_batch_multi_packed(const int* devices, int n_devices, int32_t n_pairs, const uint8_t* packed, int64_t n_bases,
+                                            const int64_t* q_off, const int32_t* q_len, const int64_t* r_off, const int32_t* r_len,
+                                            const int32_t* mask_len, const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf,
+                                            int64_t cigar_cap, int64_t* cigar_used)
+{
+    return align_multi_impl(devices, n_devices, n_pairs, reinterpret_cast<const int8_t*>(packed), n_bases, q_off, q_len, r_off, r_len,
+                            mask_len, scoring, out, cigar_buf, cigar_cap, cigar_used, true);
+}
+
+static int align_multi_impl(const int* devices, int n_devices, int32_t n_pairs, const int8_t* seqs, int64_t seqs_len,
+                            const int64_t* q_off, const int32_t* q_len, const int64_t* r_off, const int32_t* r_len,
+                            const int32_t* mask_len, const ssw_scoring* scoring, ssw_result* out, uint32_t* cigar_buf,
+                            int64_t cigar_cap, int64_t* cigar_used, bool packed)
 {
     if (cigar_used) *cigar_used = 0;
     if (n_pairs <= 0) return n_pairs == 0 ? SSW_OK : SSW_ERR_ARG;
@@ -853,6 +950,7 @@ extern "C" int ssw_align_batch_multi(const int* devices, int n_devices, int32_t 
     MultiJob J;
     J.n_pairs = n_pairs; J.chunk = chunk; J.seqs = seqs; J.seqs_len = seqs_len; J.q_off = q_off; J.q_len = q_len;
     J.r_off = r_off; J.r_len = r_len; J.mask_len = mask_len; J.scoring = scoring; J.out = out; J.cigar_buf = cigar_buf; J.cigar_cap = cigar_cap;
+    J.packed = packed;
     if (n_devices == 1) multi_worker(&J, devices[0], slots);
     else {
         std::vector<std::thread> th;

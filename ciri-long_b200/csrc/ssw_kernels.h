@@ -1,5 +1,6 @@
 // ssw_kernels.h -- launch interfaces between the host orchestration (ssw_api.cu) and the kernels.
 #pragma once
+#include <functional>
 #include "ssw_common.cuh"
 
 namespace sswb {
@@ -112,6 +113,12 @@ cudaError_t build_band_list(const BatchView& b, const Scoring& sc, const ListSet
 // ASCII letters -> codes 0..4, in place (ssw_wrap.py:234-252 on the device)
 cudaError_t encode_ascii(int8_t* seqs, long long n, cudaStream_t st);
 
+// 4-bit packed bases (two per byte, low nibble first) -> one code per byte (nibbles above 4 -> N)
+cudaError_t unpack4(const unsigned char* packed, int8_t* codes, long long n_bytes, cudaStream_t st);
+
+cudaError_t snapshot_count(int32_t* snap, const int32_t* count, cudaStream_t st);
+cudaError_t rewind_cursor(int32_t* cursor, const int32_t* snap, cudaStream_t st);
+
 // clear status bits (and the CIGAR window) of every pair, e.g. before the CIGAR pass is repeated
 cudaError_t clear_status_bits(const BatchView& b, int bits, cudaStream_t st);
 
@@ -164,14 +171,16 @@ struct TbandArgs {
 struct TbandPlan {
     int32_t row_pairs_cap, stage_cap;
     int32_t blocks[8], smem[8];
-    long long dir_bytes[8], stride[8];
+    long long dir_bytes[8], stride[8], scratch_off[8];
     long long scratch_bytes;
 };
 constexpr int TBAND_BINS = 32 * 256;
 cudaError_t tband_plan(int device, int sms, int max_q, long long budget, TbandPlan* plan);
 cudaError_t tband_configure();
+constexpr int TBAND_INSTANCES = 5;                 // side streams a batch needs: one per instance (+1 for the hand-overs)
 cudaError_t launch_tband(TbandArgs a, const TbandPlan& plan, const int32_t* in_idx, const int32_t* in_count, int n_max,
-                         int32_t* list_a, int32_t* list_b, int32_t* cnt_a, int32_t* cnt_b, cudaStream_t st, int* launches);
+                         int32_t* list_a, int32_t* list_b, int32_t* cnt_a, int32_t* cnt_b, cudaStream_t st,
+                         cudaStream_t* side, cudaEvent_t* ev, const std::function<cudaError_t(cudaEvent_t)>& after_first_sort, int* launches);
 
 // ---- batched edit distance (edit_distance.cu)
 constexpr int ED_MAXSYM = 16;          // distinct symbols per batch (4-bit codes)

@@ -211,6 +211,53 @@ cudaError_t encode_ascii(int8_t* seqs, long long n, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ---- 4-bit packed bases (two per byte, low nibble first) -> one code per byte; nibbles above 4 count as N.
+// 16 packed bytes in, 32 codes out per thread and step: 128-bit loads and stores.
+__global__ void unpack4_kernel(const unsigned char* __restrict__ packed, int8_t* __restrict__ codes, long long n_bytes)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x * 16;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < n_bytes; i += stride) {
+        if (i + 16 <= n_bytes) {
+            const uint4 v = *reinterpret_cast<const uint4*>(packed + i);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            unsigned o[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // bytes b3 b2 b1 b0 -> nibbles: low word = (b1.hi b1.lo b0.hi b0.lo), high word = (b3.hi b3.lo b2.hi b2.lo)
+                unsigned lo = (w[k] & 0xfu) | ((w[k] & 0xf0u) << 4) | ((w[k] & 0xf00u) << 8) | ((w[k] & 0xf000u) << 12);
+                unsigned hi = ((w[k] >> 16) & 0xfu) | (((w[k] >> 16) & 0xf0u) << 4) | (((w[k] >> 16) & 0xf00u) << 8) | (((w[k] >> 16) & 0xf000u) << 12);
+                o[2 * k] = __vminu4(lo, 0x04040404u);
+                o[2 * k + 1] = __vminu4(hi, 0x04040404u);
+            }
+            reinterpret_cast<uint4*>(codes + 2 * i)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<uint4*>(codes + 2 * i)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+            for (long long j = i; j < n_bytes; ++j) {
+                const unsigned b = packed[j];
+                codes[2 * j] = (int8_t)min(b & 0xfu, 4u);
+                codes[2 * j + 1] = (int8_t)min(b >> 4, 4u);
+            }
+        }
+    }
+}
+
+cudaError_t unpack4(const unsigned char* packed, int8_t* codes, long long n_bytes, cudaStream_t st)
+{
+    if (n_bytes <= 0) return cudaSuccess;
+    long long blocks = (n_bytes / 16 + 255) / 256;
+    if (blocks > 8192) blocks = 8192;
+    if (blocks < 1) blocks = 1;
+    unpack4_kernel<<<(int)blocks, 256, 0, st>>>(packed, codes, n_bytes);
+    return cudaGetLastError();
+}
+
+// A list that is still being appended to, consumed in two launches: the first launch works on a snapshot of the
+// count (its warps overshoot the fetch cursor when they leave), then the cursor is put back on the snapshot so
+// that the second launch continues exactly where the first one ended.
+__global__ void copy_int_kernel(int32_t* dst, const int32_t* src) { *dst = *src; }
+cudaError_t snapshot_count(int32_t* snap, const int32_t* count, cudaStream_t st) { copy_int_kernel<<<1, 1, 0, st>>>(snap, count); return cudaGetLastError(); }
+cudaError_t rewind_cursor(int32_t* cursor, const int32_t* snap, cudaStream_t st) { copy_int_kernel<<<1, 1, 0, st>>>(cursor, snap); return cudaGetLastError(); }
+
 __global__ void clear_status_kernel(BatchView b, int bits)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -15,6 +15,7 @@
 // Direction words go to a per-warp scratch in HBM, laid out [row pair][block][lane]: every store of the fill is
 // one full 128-byte line per warp; the traceback reads 4 bytes per step and lane.
 #include <cuda_runtime.h>
+#include <functional>
 #include "ssw_common.cuh"
 #include "ssw_kernels.h"
 #include "ssw_tband_core.h"
@@ -284,7 +285,8 @@ cudaError_t tband_plan(int device, int sms, int max_q, long long budget, TbandPl
     int smemMax = 0;
     cudaError_t e = cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
-    long long worst = 0;
+    long long total = 0;
+    budget /= TB_INST;                                    // the instances of a pass run side by side, each in its own region
     for (int inst = 0; inst < TB_INST; ++inst) {
         const int nbcap = tb_instance_nb(inst);
         const int smem = TBAND_WARPS * tband_warp_smem(nbcap);
@@ -296,9 +298,10 @@ cudaError_t tband_plan(int device, int sms, int max_q, long long budget, TbandPl
         if (blocks > fit) blocks = fit;
         if (blocks < 1) blocks = 1;
         plan->blocks[inst] = (int)blocks; plan->smem[inst] = smem; plan->dir_bytes[inst] = dirBytes; plan->stride[inst] = stride;
-        worst = worst > blocks * TBAND_WARPS * stride ? worst : blocks * TBAND_WARPS * stride;
+        plan->scratch_off[inst] = total;
+        total += blocks * TBAND_WARPS * stride;
     }
-    plan->scratch_bytes = worst;
+    plan->scratch_bytes = total;
     return cudaSuccess;
 }
 
@@ -312,27 +315,39 @@ cudaError_t tband_configure()
     return cudaFuncSetAttribute(tband_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024);   // (static: the 5x5 matrix)
 }
 
-// All passes of the CIGAR stage for the pairs of in_idx[0 .. *in_count).  Pairs this kernel cannot take end in
-// a.fallback_idx (consumed by launch_band(2, ...) afterwards).
+// All passes of the CIGAR stage for the pairs of in_idx[0 .. *in_count).  Pairs this kernel cannot take end in the
+// two hand-over lists (consumed by launch_band(1 / 2, ...)).  The instances of a pass are independent launches:
+// each runs on its own stream between two events, so a launch that is down to its last (long) lock-step rounds
+// shares the machine with the others instead of holding it.  `after_first_sort` is called once, when the first
+// pass's hand-overs are known (the caller starts the warp-per-pair instance on them, side by side).
 cudaError_t launch_tband(TbandArgs a, const TbandPlan& plan, const int32_t* in_idx, const int32_t* in_count, int n_max,
-                         int32_t* list_a, int32_t* list_b, int32_t* cnt_a, int32_t* cnt_b, cudaStream_t st, int* launches)
+                         int32_t* list_a, int32_t* list_b, int32_t* cnt_a, int32_t* cnt_b, cudaStream_t st,
+                         cudaStream_t* side, cudaEvent_t* ev, const std::function<cudaError_t(cudaEvent_t)>& after_first_sort, int* launches)
 {
     const int threads = 256, blocks = (n_max + threads - 1) / threads;
     const int32_t* cur_idx = in_idx; const int32_t* cur_cnt = in_count;
     int32_t* nxt_idx = list_a; int32_t* nxt_cnt = cnt_a;
+    cudaError_t e;
     for (int pass = 0; pass < TB_PASSES; ++pass) {
         tband_reset_kernel<<<(TB_BINS + 255) / 256, 256, 0, st>>>(a, nxt_cnt);
         tband_key_kernel<<<blocks, threads, 0, st>>>(a, pass, cur_idx, cur_cnt);
         tband_scan_kernel<<<1, 1024, 0, st>>>(a);
         tband_scatter_kernel<<<blocks, threads, 0, st>>>(a, cur_idx, cur_cnt);
         *launches += 4;
+        if ((e = cudaEventRecord(ev[TB_INST], st)) != cudaSuccess) return e;
+        if (pass == 0 && after_first_sort && (e = after_first_sort(ev[TB_INST])) != cudaSuccess) return e;
         a.next_idx = nxt_idx; a.next_count = nxt_cnt;
         for (int inst = TB_INST - 1; inst >= 0; --inst) {
             TbandArgs x = a;
+            x.scratch = a.scratch + plan.scratch_off[inst];
             x.scratch_stride = plan.stride[inst]; x.dir_bytes = plan.dir_bytes[inst];
-            tband_kernel<<<plan.blocks[inst], TBAND_WARPS * 32, plan.smem[inst], st>>>(x, inst, tb_instance_nb(inst), pass);
+            if ((e = cudaStreamWaitEvent(side[inst], ev[TB_INST], 0)) != cudaSuccess) return e;
+            tband_kernel<<<plan.blocks[inst], TBAND_WARPS * 32, plan.smem[inst], side[inst]>>>(x, inst, tb_instance_nb(inst), pass);
+            if ((e = cudaEventRecord(ev[inst], side[inst])) != cudaSuccess) return e;
             *launches += 1;
         }
+        for (int inst = 0; inst < TB_INST; ++inst)
+            if ((e = cudaStreamWaitEvent(st, ev[inst], 0)) != cudaSuccess) return e;
         cur_idx = nxt_idx; cur_cnt = nxt_cnt;
         if (nxt_idx == list_a) { nxt_idx = list_b; nxt_cnt = cnt_b; } else { nxt_idx = list_a; nxt_cnt = cnt_a; }
     }

@@ -53,6 +53,7 @@ def _owner_main(device, req_q, resp_qs, req_names, resp_names, arena_bytes, max_
     ready.put("ok")
     stats = dict(batches=0, pairs=0, requests=0)
     pending, stop = [], False
+    parts = q_len = r_len = seqs = None
     while not stop or pending:
         # ---- collect announcements: block for the first, then until the batch is full or flush_ms has passed
         if not pending:
@@ -129,9 +130,13 @@ def _owner_main(device, req_q, resp_qs, req_names, resp_names, arena_bytes, max_
                         np.frombuffer(out, dtype=np.uint32, count=len(cflat), offset=r.nbytes)[:] = cflat
                     resp_qs[slot].put(("ok", n, len(cflat)))
                 p0 += n
-    for s in reqs + resps:
-        s.close()
     ready.put(stats)
+    del parts, q_len, r_len, seqs
+    for s in reqs + resps:
+        try:
+            s.close()
+        except BufferError:
+            pass                                     # (views into the arena still referenced by the last batch)
 
 
 class AlignClient(object):

@@ -111,6 +111,12 @@ def _load():
     lib.ssw_align_batch_multi.restype = c_int
     lib.ssw_align_batch_multi.argtypes = [c_void_p, c_int, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, POINTER(SSWScoring), c_void_p, c_void_p, c_int64, POINTER(c_int64)]
+    lib.ssw_align_batch_multi_packed.restype = c_int
+    lib.ssw_align_batch_multi_packed.argtypes = lib.ssw_align_batch_multi.argtypes
+    lib.ssw_batch_create_packed.restype = c_void_p
+    lib.ssw_batch_create_packed.argtypes = lib.ssw_batch_create.argtypes
+    lib.ssw_pack_dna4.restype = None
+    lib.ssw_pack_dna4.argtypes = [c_void_p, c_int64, c_void_p]
     lib.ssw_cuda_trim_pools.restype = c_int
     lib.ssw_cuda_last_error.restype = c_char_p
     lib.ssw_cuda_device_count.restype = c_int
@@ -138,6 +144,15 @@ class SSWCudaError(RuntimeError):
     pass
 
 
+def pack_dna4(codes):
+    """codes 0..4 (one per byte) -> two bases per byte, low nibble first: the input of the *_packed entry points
+    (half the host-to-device bytes; offsets and lengths keep counting bases)."""
+    codes = np.ascontiguousarray(codes, dtype=np.int8)
+    out = np.zeros((len(codes) + 1) // 2, dtype=np.uint8)
+    Aligner.libssw.ssw_pack_dna4(codes.ctypes.data, len(codes), out.ctypes.data)
+    return out
+
+
 # Opt-in: route this process's alignments through a GPU-owner service (server.py) instead of the local library.
 # Meant for forked pool workers (find_bsj.py:338-345, collapse.py:842-851), which must not create CUDA contexts of
 # their own: ``Aligner.align`` then blocks on the service, so unmodified call sites batch across workers.
@@ -157,8 +172,9 @@ class DeviceBatch(object):
     libssw = _load()
 
     def __init__(self, seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend,
-                 flag=1, mask_len=None, device=0, stream=None, filters=0, filterd=0, ascii=False):
-        self.seqs = np.ascontiguousarray(seqs, dtype=np.int8)
+                 flag=1, mask_len=None, device=0, stream=None, filters=0, filterd=0, ascii=False, packed_bases=0):
+        # packed_bases > 0: `seqs` is a 4-bit packed buffer (pack_dna4) holding that many bases
+        self.seqs = np.ascontiguousarray(seqs, dtype=np.uint8 if packed_bases else np.int8)
         self.q_off = np.ascontiguousarray(q_off, dtype=np.int64)
         self.q_len = np.ascontiguousarray(q_len, dtype=np.int32)
         self.r_off = np.ascontiguousarray(r_off, dtype=np.int64)
@@ -167,8 +183,9 @@ class DeviceBatch(object):
         self.n = len(self.q_len)
         self.flag = flag
         self.scoring = make_scoring(match, mismatch, gap_open, gap_extend, flag, filters, filterd)
-        self.handle = self.libssw.ssw_batch_create(
-            device, stream, self.n, self.seqs.ctypes.data, self.seqs.size,
+        create = self.libssw.ssw_batch_create_packed if packed_bases else self.libssw.ssw_batch_create
+        self.handle = create(
+            device, stream, self.n, self.seqs.ctypes.data, packed_bases if packed_bases else self.seqs.size,
             self.q_off.ctypes.data, self.q_len.ctypes.data, self.r_off.ctypes.data, self.r_len.ctypes.data,
             None if self.mask_len is None else self.mask_len.ctypes.data, byref(self.scoring))
         if not self.handle:
@@ -538,12 +555,13 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
 
 
 def align_arrays(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend, flag=1, mask_len=None,
-                 device=0, out=None, cig=None, devices=None, filters=0, filterd=0):
+                 device=0, out=None, cig=None, devices=None, filters=0, filterd=0, packed_bases=0):
     """The one-shot C call (ssw_align_batch / ssw_align_batch_multi) on struct-of-arrays host buffers: upload, all
     kernels and download in one call, chunk-pipelined inside the library.  ``devices=[0, 1, ...]`` spreads the
     chunks over several GPUs of the box (one host thread per device, results gathered at the pairs' indices;
-    bit-identical to the single-device call).  Returns (records, cigar ops)."""
-    seqs = np.ascontiguousarray(seqs, dtype=np.int8)
+    bit-identical to the single-device call).  ``packed_bases=n``: `seqs` is a 4-bit packed buffer (pack_dna4) of n
+    bases -- half the upload.  Returns (records, cigar ops)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8 if packed_bases else np.int8)
     q_off = np.ascontiguousarray(q_off, dtype=np.int64); r_off = np.ascontiguousarray(r_off, dtype=np.int64)
     q_len = np.ascontiguousarray(q_len, dtype=np.int32); r_len = np.ascontiguousarray(r_len, dtype=np.int32)
     n = len(q_len)
@@ -555,7 +573,8 @@ def align_arrays(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, ga
     used = c_int64(0)
     ml = None if mask_len is None else np.ascontiguousarray(mask_len, dtype=np.int32)
     devs = np.ascontiguousarray([device] if devices is None else list(devices), dtype=np.int32)
-    rc = Aligner.libssw.ssw_align_batch_multi(devs.ctypes.data, len(devs), n, seqs.ctypes.data, seqs.size, q_off.ctypes.data,
+    call = Aligner.libssw.ssw_align_batch_multi_packed if packed_bases else Aligner.libssw.ssw_align_batch_multi
+    rc = call(devs.ctypes.data, len(devs), n, seqs.ctypes.data, packed_bases if packed_bases else seqs.size, q_off.ctypes.data,
                                               q_len.ctypes.data, r_off.ctypes.data, r_len.ctypes.data,
                                               None if ml is None else ml.ctypes.data, byref(sc), out.ctypes.data,
                                               cig.ctypes.data, len(cig), byref(used))

@@ -157,6 +157,22 @@ int ssw_align_batch_multi(const int* devices, int n_devices, int32_t n_pairs, co
                           const int32_t* mask_len, const ssw_scoring* scoring,
                           ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
 
+/* 4-bit packed input (north_star: packed bases, 128-bit loads; SURVEY.md section 0 item 6: N needs its own code, so
+ * 4 bits, not 2).  `packed` holds two bases per byte, low nibble first, codes 0..4 (A C G T N; anything above 4
+ * counts as N); offsets and lengths count BASES into that buffer.  Half the bytes cross PCIe; the device expands
+ * them with 128-bit loads/stores into the one-code-per-byte layout the kernels read.  Results are identical to the
+ * unpacked calls.  ssw_pack_dna4 is the host-side packer (codes -> nibbles). */
+ssw_batch* ssw_batch_create_packed(int device, void* stream, int32_t n_pairs, const uint8_t* packed, int64_t n_bases,
+                                   const int64_t* q_off, const int32_t* q_len,
+                                   const int64_t* r_off, const int32_t* r_len,
+                                   const int32_t* mask_len, const ssw_scoring* scoring);
+int ssw_align_batch_multi_packed(const int* devices, int n_devices, int32_t n_pairs, const uint8_t* packed, int64_t n_bases,
+                                 const int64_t* q_off, const int32_t* q_len,
+                                 const int64_t* r_off, const int32_t* r_len,
+                                 const int32_t* mask_len, const ssw_scoring* scoring,
+                                 ssw_result* out, uint32_t* cigar_buf, int64_t cigar_cap, int64_t* cigar_used);
+void ssw_pack_dna4(const int8_t* codes, int64_t n, uint8_t* packed);
+
 /* ASCII -> {0..4} on the device-facing side of the boundary: vectorised replacement for the
  * per-base Python loop of ssw_wrap.py:234-252 (A C G T N, either case; anything else -> 4). */
 void ssw_encode_dna(const char* ascii, int64_t len, int8_t* codes);

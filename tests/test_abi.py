@@ -27,7 +27,8 @@ def test_exports_every_declared_symbol(sw):
     names -= {"ssw_scoring", "ssw_result", "ssw_batch"}
     assert {"ssw_init", "ssw_align", "init_destroy", "align_destroy", "cigar_int_to_op", "cigar_int_to_len",
             "ssw_batch_create", "ssw_batch_run", "ssw_batch_fetch", "ssw_batch_destroy", "ssw_align_batch", "ssw_align_batch_multi",
-            "ssw_batch_stage_ms", "ssw_encode_dna", "ssw_cuda_dpx_peak"} <= names
+            "ssw_batch_stage_ms", "ssw_encode_dna", "ssw_cuda_dpx_peak", "ssw_batch_create_packed", "ssw_align_batch_multi_packed",
+            "ssw_pack_dna4", "ssw_cuda_trim_pools"} <= names
     lib = ctypes.CDLL(os.path.join(ROOT, "ciri-long_b200", "libssw_cuda.so"))
     for n in sorted(names):
         assert hasattr(lib, n), n
@@ -106,3 +107,10 @@ def test_revcomp_matches_the_reference_table(sw):
     assert cs.revcomp("AAccGG") == "CCccTT"                     # lower case reversed, not complemented
     window = "ACGTacgtNNACGT"
     assert cs.revcomp(window) == "ACGTNNtgcaACGT"
+
+
+def test_pack_dna4_layout(sw):
+    """two bases per byte, low nibble first; codes above 4 become N (4); odd lengths leave the last high nibble 0"""
+    c = np.array([0, 1, 2, 3, 4, 3, 2], dtype=np.int8)
+    assert sw.pack_dna4(c).tolist() == [0 | 1 << 4, 2 | 3 << 4, 4 | 3 << 4, 2]
+    assert sw.pack_dna4(np.array([7, -1], dtype=np.int8)).tolist() == [4 | 4 << 4]

@@ -167,3 +167,40 @@ def test_band_escape_returns_coordinates_and_empty_cigar(sw, monkeypatch, lane_k
             (e["score"], e["ref_begin"], e["ref_end"], e["read_begin"], e["read_end"])
         res2 = sw.align_pairs([c["ref"]], [c["query"]], *p, report_cigar=True)[0]
         assert res2 is not None and res2.cigar_string is None and res2.ref_begin == e["ref_begin"]
+
+
+def test_packed_input_matches_unpacked(sw):
+    """ssw_batch_create_packed / ssw_align_batch_multi_packed (two bases per byte, offsets in bases, odd offsets and
+    lengths, N bases) give the records and CIGARs of the one-code-per-byte calls"""
+    from ciri_long_b200 import workloads as W
+    parts = [W.bsj_refinement_pairs(700, seed=41, params=(10, 4, 8, 2)), W.junction_pairs(900, seed=42), W.square_pairs(60, 333, params=(10, 4, 8, 2))]
+    b = W.concat_batches(parts, shuffle_seed=3)
+    packed = sw.pack_dna4(b.seqs)
+    with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, 10, 4, 8, 2) as d:
+        d.run(); r1, c1 = d.fetch()
+    with sw.DeviceBatch(packed, b.q_off, b.q_len, b.r_off, b.r_len, 10, 4, 8, 2, packed_bases=len(b.seqs)) as d:
+        d.run(); r2, c2 = d.fetch()
+    r3, c3 = sw.align_arrays(packed, b.q_off, b.q_len, b.r_off, b.r_len, 10, 4, 8, 2, packed_bases=len(b.seqs))
+    for ra, ca in ((r2, c2), (r3, c3)):
+        for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len", "status", "word"):
+            assert (r1[k] == ra[k]).all(), k
+        for i in range(len(b)):
+            assert (c1[r1["cigar_off"][i]:r1["cigar_off"][i] + r1["cigar_len"][i]] == ca[ra["cigar_off"][i]:ra["cigar_off"][i] + ra["cigar_len"][i]]).all()
+
+
+def test_multi_device_call_matches_single_device(sw, monkeypatch):
+    """ssw_align_batch_multi over all devices of the box (chunks pulled from a shared queue by one host thread per
+    device) = the single-device call, pair by pair; with one device it degenerates to several chunks in flight"""
+    from ciri_long_b200 import workloads as W
+    ndev = sw.Aligner.libssw.ssw_cuda_device_count()
+    monkeypatch.setenv("SSW_CUDA_CHUNK", "3000")                   # many chunks, so that every device gets several
+    monkeypatch.setenv("SSW_CUDA_TBAND_MIN", "1024")
+    b = W.concat_batches([W.bsj_refinement_pairs(9000, seed=43), W.junction_pairs(12000, seed=44, params=(1, 1, 1, 1))], shuffle_seed=9)
+    b = W.repack(b)
+    r1, c1 = sw.align_arrays(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, 1, 1, 1, 1, device=0)
+    r2, c2 = sw.align_arrays(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, 1, 1, 1, 1, devices=list(range(ndev)) if ndev > 1 else [0])
+    for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len", "status", "word"):
+        assert (r1[k] == r2[k]).all(), k
+    for i in range(0, len(b), 7):
+        assert (c1[r1["cigar_off"][i]:r1["cigar_off"][i] + r1["cigar_len"][i]] == c2[r2["cigar_off"][i]:r2["cigar_off"][i] + r2["cigar_len"][i]]).all()
+    assert len(c1) == len(c2) == int(r1["cigar_len"].sum())

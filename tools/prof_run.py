@@ -9,7 +9,11 @@ kind = sys.argv[3] if len(sys.argv) > 3 else "c2"
 if kind == "c2":
     b = W.bsj_refinement_pairs(n, seed=5)
 elif kind == "c3":
-    b = W.rolling_circle_pairs(n, seed=5)
+    import torch
+    b = W.repack(W.rolling_circle_pairs_torch(n, torch.device("cuda", 0), seed=5))
+elif kind == "c5":
+    import torch
+    b = W.mixed_slab_torch(n, torch.device("cuda", 0), seed=5)
 else:
     b = W.square_pairs(n, int(kind), params=(10, 4, 8, 2))
 with sw.DeviceBatch(b.seqs, b.q_off, b.q_len, b.r_off, b.r_len, b.match, b.mismatch, b.gap_open, b.gap_extend, flag=1) as d:
