@@ -176,13 +176,26 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
 
     int candM = 0, candCol = -1, candRow = 0;
     int termCol = -1, overCol = 0x7fffffff;
-    // Reverse pass only: if a cell above score1 turns up at or before the stop column (the two truncated-F
-    // passes disagree), the pass is repeated in exact mode: limited to the columns the reference visits
-    // (ssw.c:296,499 break) and with plain best-cell tracking.
+    // Reverse pass only, three ways to run it:
+    //   fast     (single-tile queries): no best-cell tracking at all.  The answer is the first column whose maximum
+    //            equals score1 (ssw.c:296,499) and the first row in it that holds score1, so every strip only notes
+    //            the first column in which one of its rows reaches score1 exactly (and the row); cells above
+    //            score1 are noted like below.  If no column reaches score1 the tracking way decides.
+    //   tracking plain best-cell tracking, cells above score1 kept out of it and only their first column noted.
+    //   exact    if a cell above score1 turns up at or before the stop column (the two truncated-F passes
+    //            disagree): limited to the columns the reference visits, plain best-cell tracking.
+    constexpr int RM_FAST = 0, RM_TRACK = 1, RM_EXACT = 2;
+    // (not for the truncated-F recurrence: its reverse pass often stays below score1 -- the segment borders fall on
+    // other rows than in the forward pass --, and a fast pass that finds nothing has to be repeated with tracking)
+    int mode = (REV && !CHUNK && !TRUNC && T == 1) ? RM_FAST : RM_TRACK;
     bool exactMode = false;
+    const unsigned mterm1P = pack2(1 - (terminate + go), 1 - (terminate + go));
+    int hitColLo = -1, hitColHi = -1, hitRowLo = 0, hitRowHi = 0;
 
-    for (int attempt = 0; attempt < (REV ? 2 : 1); ++attempt) {
+    for (;;) {
+    exactMode = mode == RM_EXACT;
     candM = 0; candCol = -1; candRow = 0; termCol = -1; overCol = 0x7fffffff;
+    hitColLo = -1; hitColHi = -1;
     for (int p = 0; p < T; ++p) {
         const bool lastTile = (p == T - 1);
         const StripGeom sLo = strip_geom<K, TRUNC>(p * VSTRIPS + lane, Vtot, dead, segLen, G, base, extra);
@@ -226,9 +239,10 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
         //   CHECK = some lane may be outside [0, n) (pipeline fill and drain)
         //   MULTI = the query spans several tiles: strip 0 may continue below the previous tile (boundary
         //           array in), the last strip may feed the next tile (boundary array out)
-        auto step = [&](auto chk, auto multi, const int s, const int t) {
+        auto step = [&](auto chk, auto multi, auto fastc, const int s, const int t) {
             constexpr bool CHECK = decltype(chk)::value;
             constexpr bool MULTI = decltype(multi)::value;
+            constexpr bool FAST = REV && decltype(fastc)::value;
             // hand-off from the previous strip (computed one step ago, same column as ours now)
             unsigned rH = __byte_perm(__shfl_sync(FULL, Hout, src), GO, fix);
             unsigned rF = __byte_perm(__shfl_sync(FULL, Fout, src), GO, fix);
@@ -288,7 +302,25 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             }
             if (TRUNC) mxv &= stripMask;
             R = max_relu(rR, mxv);
-            if (REV && !exactMode) {
+            if (FAST) {
+                const unsigned reach = addmax_relu(mxv, mterm1P, 0u);          // max(mxv - score1 + 1, 0) per half
+                if (reach) {
+                    const int vl = lo16(mxv) - go, vh = hi16(mxv) - go;
+                    if (vl > terminate) overCol = cLo < overCol ? cLo : overCol;
+                    else if (vl == terminate && hitColLo < 0) {
+                        hitColLo = cLo;
+#pragma unroll
+                        for (int i = K - 1; i >= 0; --i) if (i < sLo.live && lo16(Hd[i]) - go == terminate) hitRowLo = sLo.first + i;
+                    }
+                    if (vh > terminate) overCol = cHi < overCol ? cHi : overCol;
+                    else if (vh == terminate && hitColHi < 0) {
+                        hitColHi = cHi;
+#pragma unroll
+                        for (int i = K - 1; i >= 0; --i) if (i < sHi.live && hi16(Hd[i]) - go == terminate) hitRowHi = sHi.first + i;
+                    }
+                }
+            }
+            if (REV && !FAST && !exactMode) {
                 // The reference stops at the first column whose maximum equals score1 (ssw.c:296,499), so
                 // cells above score1 only count if they occur before that column.  Strips ahead of the
                 // stop column keep running here: values above score1 are kept out of the best-cell
@@ -305,9 +337,10 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                     if (hi16(mxv) - go > terminate) { if (!CHUNK || cHi >= skipc) overCol = cHi < overCol ? cHi : overCol; mxv &= 0x0000ffffu; }
                 }
             }
-            bool pHi, pLo;
-            const unsigned nb = __vibmax_s16x2(bestT, mxv, &pHi, &pLo);  // pred = (bestT >= mxv)
-            if (!(pHi && pLo)) {
+            bool pHi = true, pLo = true;
+            unsigned nb = 0;
+            if (!FAST) nb = __vibmax_s16x2(bestT, mxv, &pHi, &pLo);      // pred = (bestT >= mxv)
+            if (!FAST && !(pHi && pLo)) {
                 // (chunk mode: warm-up columns, c < skip, are not recorded and do not raise the threshold)
                 const int skip = CHUNK ? ckw[0] : 0;
                 unsigned acc = 0;
@@ -352,7 +385,8 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
             // the first column, ssw.c:286-292), and a strip that is ahead in time can be behind in columns
             bestT = max_relu(bestT, pack2(g - 1, g - 1));
         };
-        auto sweep = [&](auto multi) {
+        auto sweep = [&](auto multi, auto fastc) {
+            constexpr bool FASTS = REV && decltype(fastc)::value;
             int s0 = 0;
             bool stop = false;
             while (s0 < steps && !stop) {
@@ -386,20 +420,22 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
                 if (steady) {
 #pragma unroll 8
                     for (int t = 0; t < len; ++t) {
-                        step(std::false_type{}, multi, s0 + t, t);
+                        step(std::false_type{}, multi, fastc, s0 + t, t);
                         if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
-                        if ((t & 31) == 31) refresh();
+                        if (!FASTS && (t & 31) == 31) refresh();
                     }
                 } else {
                     for (int t = 0; t < len; ++t) {
-                        step(std::true_type{}, multi, s0 + t, t);
+                        step(std::true_type{}, multi, fastc, s0 + t, t);
                         if (REV && lastTile && (t & 7) == 7 && __any_sync(FULL, termflag)) { stop = true; break; }
                     }
                 }
                 s0 = s1;
             }
         };
-        if (T > 1) sweep(std::true_type{}); else sweep(std::false_type{});
+        if (T > 1) sweep(std::true_type{}, std::false_type{});
+        else if (REV && mode == RM_FAST) sweep(std::false_type{}, std::true_type{});
+        else sweep(std::false_type{}, std::false_type{});
 
         // ---- tile epilogue: best cell of this tile in reference order (max, first column, first row)
         const int vlo = lo16(best) - go, vhi = hi16(best) - go;
@@ -432,10 +468,18 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int pair, c
     if (REV && !exactMode) {
         overCol = __reduce_min_sync(FULL, overCol);
         if (overCol != 0x7fffffff && (termCol < 0 || overCol <= termCol)) {
-            exactMode = true;
+            mode = RM_EXACT;
             if (termCol >= 0) n = termCol + 1;
             continue;
         }
+    }
+    if (REV && mode == RM_FAST) {
+        // the first row that holds score1 in the stop column, over the strips that met score1 there
+        const int rl = (termCol >= 0 && hitColLo == termCol) ? hitRowLo : 0x7fffffff;
+        const int rh = (termCol >= 0 && hitColHi == termCol) ? hitRowHi : 0x7fffffff;
+        const int row = __reduce_min_sync(FULL, rl < rh ? rl : rh);
+        if (row == 0x7fffffff) { mode = RM_TRACK; continue; }             // score1 never reached: plain tracking decides
+        candM = terminate; candCol = termCol; candRow = row > m - 1 ? m - 1 : row;
     }
     break;
     }
