@@ -137,7 +137,8 @@ struct ssw_batch {
     int max_q = 0, max_r = 0, maxK = 0;
     int max_rows = 0;                    // bound on the rows of any pair's trimmed rectangle (CIGAR scratch)
     bool have[2][2][KMAX + 1];           // forward lists known to be non-empty: [cls][kind][K]
-    bool have_t2[2][KMAX + 1];           // GOTOH-first pairs that may overflow and move on to TRUNC: [cls][K]
+    bool have_t2[2][KMAX + 1];
+    int32_t n_tiny = 0;                  // pairs of the one-pair-per-thread score kernel (ssw_tiny.cu)           // GOTOH-first pairs that may overflow and move on to TRUNC: [cls][K]
     // long references (class 1): forward pass over column chunks (ssw_kernels.h: ChunkPlan)
     int32_t chunk_cols = 0;
     int32_t long_pairs[2][KMAX + 1];     // class-1 pairs per forward list [kind][K]
@@ -242,7 +243,12 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->max_r = std::max(b->max_r, r);
         lo = std::min<long long>(lo, std::min(q_off[p], r_off[p]));
         hi = std::max<long long>(hi, std::max(q_off[p] + m, r_off[p] + r));
-        if (m > 0 && r > 0) {
+        if (is_tiny_pair(m, r, maxScore, b->sc.bias)) {
+            b->n_tiny += 1;
+            cig_worst += 2LL * m + 3;
+            q_total += m;
+            b->max_rows = std::max<int>(b->max_rows, m);
+        } else if (m > 0 && r > 0) {
             const int kind = first_pass_kind(m, b->sc.go, b->sc.ge, maxScore, b->sc.bias);
             const int K = strip_height_for(m, kind);
             b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
@@ -589,6 +595,14 @@ extern "C" int ssw_batch_run(ssw_batch* b)
     // ---- forward pass
     CU_TRY(cudaEventRecord(b->ev[0], st));
     CU_TRY(build_lists(0, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
+    if (b->n_tiny > 0) {
+        TinyArgs ta;
+        ta.b = view; ta.sc = b->sc;
+        ta.wl = WorkList{ls.idx, ls.base + LIST_TINY, ls.count + LIST_TINY, ls.cursor + LIST_TINY};
+        const int blocks = (int)std::min<long long>(((long long)b->n_tiny + 127) / 128, (long long)b->sms * 16);
+        CU_TRY(launch_tiny(ta, blocks, st));
+        ++launches;
+    }
     for (int cls = 0; cls < 2; ++cls)
         for (int kind = 0; kind < 2; ++kind)
             for (int K = 1; K <= KMAX; ++K) {
@@ -632,7 +646,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         }
     // ---- pairs whose score left the 16-bit comfort zone: 32-bit kernels (rare)
     const int wcls = b->d_sscr[1] ? 1 : 0;
-    for (int kind = 0; kind < 2; ++kind) {
+    for (int kind = 0; kind < 2 && b->d_sscr[wcls]; ++kind) {            // (no scratch = nothing but tiny pairs in the batch)
         ScoreArgs a = score_args(wcls);
         a.wl = WorkList{b->d_idx3 + (size_t)kind * nn3, nullptr, b->count2() + LIST_WIDE32 + 2 + kind, b->cursor2() + LIST_WIDE32 + 2 + kind};
         CU_TRY(launch_score32(kind == 1, false, a, b->sblocks[wcls], st));
@@ -677,7 +691,7 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                 }
             }
         }
-        for (int kind = 0; kind < 2; ++kind) {
+        for (int kind = 0; kind < 2 && b->d_sscr[wcls]; ++kind) {
             const int id = LIST_WIDE32 + kind;
             ScoreArgs a = score_args(wcls);
             a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};

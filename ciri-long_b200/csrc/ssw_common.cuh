@@ -32,7 +32,8 @@ enum : int32_t {
     PS_BAND_SCRATCH = 8,    // direction matrix did not fit the per-warp scratch
     PS_CIGAR_CAP = 16,      // cigar output buffer exhausted
     PS_UNSUPPORTED = 32,
-    PS_WIDE32 = 64          // scores near the 16-bit range: handled by the 32-bit score kernels
+    PS_WIDE32 = 64,         // scores near the 16-bit range: handled by the 32-bit score kernels
+    PS_REV_DONE = 128       // begin coordinates already computed (tiny pairs: ssw_tiny.cu does both passes)
 };
 
 // one record per pair, device resident (mirrors ssw_result + internals)

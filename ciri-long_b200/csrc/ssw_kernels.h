@@ -89,8 +89,21 @@ __host__ __device__ inline int strip_height_for(int m, int trunc)
 
 // ---- work-list construction (ssw_lists.cu)
 // list id = cls * 34 + kind * 17 + K   (cls: 0 normal / 1 long reference; kind: 0 GOTOH / 1 TRUNC; K: 1..16)
-constexpr int N_LISTS = 2 * 2 * 17 + 4;           // + 68/69: reverse lists of the 32-bit kernels; 70/71: their forward counters
+constexpr int N_LISTS = 2 * 2 * 17 + 5;           // + 68/69: reverse lists of the 32-bit kernels; 70/71: their forward counters; 72: tiny pairs
 constexpr int LIST_WIDE32 = 68;
+constexpr int LIST_TINY = 72;
+// ---- tiny pairs: one pair per thread, forward + reverse fused (ssw_tiny.cu)
+constexpr int TINY_LEN = 64;                      // both sequences at most this long ...
+__host__ __device__ inline bool is_tiny_pair(int m, int n, int maxScore, int bias)
+{   // ... and a score that cannot leave the 8-bit range: the byte flavour answers (ssw.c:805-809)
+    return m >= 1 && n >= 1 && m <= TINY_LEN && n <= TINY_LEN && (long long)(m < n ? m : n) * maxScore + bias < 255;
+}
+struct TinyArgs {
+    BatchView b;
+    Scoring sc;
+    WorkList wl;
+};
+cudaError_t launch_tiny(const TinyArgs& a, int blocks, cudaStream_t st);
 __host__ __device__ inline int list_id(int cls, int kind, int K) { return cls * 34 + kind * 17 + K; }
 
 struct ListSet {

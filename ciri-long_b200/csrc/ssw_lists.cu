@@ -19,11 +19,12 @@ __device__ int classify(int stage, const BatchView& b, const Scoring& sc, int lo
         const int m = b.q_len[p], n = b.r_len[p];
         if (m <= 0 || n <= 0) return -1;
         // the word flavour with gap_open == gap_extend has its own recurrence (TRUNC); which one goes first is a guess
+        if (is_tiny_pair(m, n, maxScore, sc.bias)) return LIST_TINY;
         const int kind = first_pass_kind(m, sc.go, sc.ge, maxScore, sc.bias);
         return list_id(n > long_thr ? 1 : 0, kind, strip_height(m, kind));
     }
     // stage 1: reverse pass (ssw.c:834)
-    if (rec->status & (PS_PUNT | PS_UNSUPPORTED)) return -1;
+    if (rec->status & (PS_PUNT | PS_UNSUPPORTED | PS_REV_DONE)) return -1;
     if (sc.flag == 0 || (sc.flag == 2 && rec->score1 < sc.filters)) return -1;
     const int m = rec->read_end1 + 1, n = rec->ref_end1 + 1;
     if (n <= 0) return -2;          // score 0: nothing to walk (handled inline by the caller)
