@@ -233,7 +233,8 @@ def make_batches(cfg_name, args, dev, rank, world):
         per = n // C5_SLABS
         # the same 8 slabs whatever the number of ranks; statistically identical, so dealing them round-robin is
         # the cost-balanced (LPT) assignment
-        return [W.mixed_slab_torch(per, dev, seed=W.SEED_BASE + 50 + 10 * s, params=p) for s in range(C5_SLABS) if s % world == rank]
+        slabs = [W.mixed_slab_torch(per, dev, seed=W.SEED_BASE + 50 + 10 * s, params=p) for s in range(C5_SLABS) if s % world == rank]
+        return [W.concat_batches(slabs, name="C5-mixed")]          # this rank's share as ONE batch (one set of device scratch)
     raise SystemExit("unknown config " + cfg_name)
 
 

@@ -224,8 +224,10 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         // enough tasks to fill the machine a few times over, chunks long enough to amortise the overlap
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+        // (a launch cannot end before its longest task does, and every strip-height list is its own launch: 16 k
+        // columns keep that tail at a few ms while the warm-up overlap of a task stays below ~10 %)
         long long c = long_cols / (8LL * std::max(sms, 1) * SCORE_WARPS);
-        c = std::max<long long>(8192, std::min<long long>(c, 65536));
+        c = std::max<long long>(8192, std::min<long long>(c, 16384));
         b->chunk_cols = (int32_t)((c + RP_CHUNK - 1) / RP_CHUNK * RP_CHUNK);
     }
     memset(b->task_cap, 0, sizeof b->task_cap);
@@ -356,7 +358,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->use_tband = n >= tband_min;
         long long blocks = 0;
         if (b->use_tband) {
-            long long budget = 16LL << 30;               // direction words of the resident lock-step rounds (HBM: 180 GB)
+            long long budget = 12LL << 30;               // direction words of the resident lock-step rounds (HBM: 180 GB)
             if (const char* e = getenv("SSW_CUDA_TBAND_BUDGET_MB")) { const long v = atol(e); if (v > 0) budget = (long long)v << 20; }
             CU_TRY(tband_plan(b->device, b->sms, b->max_rows, budget, &b->tplan));
             CU_TRY(tband_configure());
@@ -378,7 +380,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->wdir = std::min<long long>(1024LL * rows + 65536, 64LL << 20);
         b->wstride = ((long long)b->bstage * 4 + b->wdir + 255) & ~255LL;
         blocks = std::min<long long>((long long)b->sms * 2, (n + BAND_WARPS - 1) / BAND_WARPS);
-        blocks = std::max<long long>(1, std::min<long long>(blocks, (b->use_tband ? 8LL << 30 : SCRATCH_BUDGET) / (b->wstride * BAND_WARPS)));
+        blocks = std::max<long long>(1, std::min<long long>(blocks, (b->use_tband ? 4LL << 30 : SCRATCH_BUDGET) / (b->wstride * BAND_WARPS)));
         b->wblocks = (int)blocks;
         CU_TRY(dev_alloc_t(&b->d_wscr, (size_t)(blocks * BAND_WARPS * b->wstride), st));
         // CIGAR output: the worst case is 2*len(query)+3 ops per pair; real alignments need a small

@@ -11,6 +11,9 @@ if kind == "c2":
 elif kind == "c3":
     import torch
     b = W.repack(W.rolling_circle_pairs_torch(n, torch.device("cuda", 0), seed=5))
+elif kind == "s2":
+    import torch
+    b = W.junction_pairs_torch(n, torch.device("cuda", 0), seed=5)
 elif kind == "c5":
     import torch
     b = W.mixed_slab_torch(n, torch.device("cuda", 0), seed=5)
