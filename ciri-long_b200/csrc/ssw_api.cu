@@ -6,6 +6,7 @@
 // Legacy interface: the six symbols of the reference libssw.so (ssw.h:72-182) as a batch of one pair.
 // There is no CPU implementation of the alignment in this file or behind it.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -156,7 +157,7 @@ struct ssw_batch {
     long long rev_task_total = 0;
     int32_t long_total = 0;              // class-1 pairs in the batch
     int64_t launches = 0;
-    std::vector<PairRec> h_rec;
+    PairRec* h_rec = nullptr;            // the caller's result array during a fetch: ssw_result and PairRec share their layout
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries of the last run
 
     BatchView view() const { return BatchView{d_seqs - seq_lo, d_qoff, d_qlen, d_roff, d_rlen, d_mask, d_rec, n}; }
@@ -234,45 +235,87 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
     std::vector<int64_t> h_col_off;
     long long col_total = 0;
     if (b->chunk_cols) h_col_off.assign(n, 0);
-    for (int32_t p = 0; p < n; ++p) {
-        const int m = q_len[p], r = r_len[p];
-        if (m < 0 || r < 0 || q_off[p] < 0 || r_off[p] < 0 || q_off[p] + m > seqs_len || r_off[p] + r > seqs_len) {
-            set_error("pair " + std::to_string(p) + ": offsets/lengths outside the sequence buffer");
-            return SSW_ERR_ARG;
+    // Shape summary of the batch (which kernel instances it needs, scratch bounds, byte range to upload).  One pass
+    // over the pairs, on several host threads for large batches: with millions of tiny pairs this loop, not the
+    // GPU, would otherwise set the pace of the one-shot call.
+    struct Part {
+        bool have[2][2][KMAX + 1] = {}; bool have_t2[2][KMAX + 1] = {};
+        int32_t long_pairs[2][KMAX + 1] = {}; long long task_cap[2][KMAX + 1] = {};
+        int32_t n_tiny = 0, long_total = 0, bad = -1;
+        int max_q = 0, max_r = 0, max_rows = 0, maxK = 0;
+        long long cig_worst = 0, q_total = 0, rev_task_total = 0, lo = 0, hi = 0;
+    };
+    const Scoring sc = b->sc;
+    const int32_t chunk_cols = b->chunk_cols;
+    int32_t* h_mask = b->h_mask.data();
+    auto scan = [&](int32_t p0, int32_t p1, Part& P) {
+        P.lo = seqs_len; P.hi = 0;
+        for (int32_t p = p0; p < p1; ++p) {
+            const int m = q_len[p], r = r_len[p];
+            if (m < 0 || r < 0 || q_off[p] < 0 || r_off[p] < 0 || q_off[p] + m > seqs_len || r_off[p] + r > seqs_len) { if (P.bad < 0) P.bad = p; continue; }
+            h_mask[p] = mask_len ? mask_len[p] : (m > 30 ? m / 2 : 15);      // ssw_wrap.py:196-199
+            P.max_q = std::max(P.max_q, m);
+            P.max_r = std::max(P.max_r, r);
+            P.lo = std::min<long long>(P.lo, std::min(q_off[p], r_off[p]));
+            P.hi = std::max<long long>(P.hi, std::max(q_off[p] + m, r_off[p] + r));
+            if (is_tiny_pair(m, r, maxScore, sc.bias)) {
+                P.n_tiny += 1;
+                P.cig_worst += 2LL * m + 3;
+                P.q_total += m;
+                P.max_rows = std::max<int>(P.max_rows, m);
+            } else if (m > 0 && r > 0) {
+                const int kind = first_pass_kind(m, sc.go, sc.ge, maxScore, sc.bias);
+                const int K = strip_height_for(m, kind);
+                const int cls = r > LONG_REF_THRESHOLD ? 1 : 0;
+                P.have[cls][kind][K] = true;
+                if (cls) {
+                    P.long_pairs[kind][K] += 1;
+                    P.task_cap[kind][K] += chunk_tasks(m, r, chunk_cols, maxScore, sc.ge);
+                    P.long_total += 1;
+                    P.rev_task_total += (r + chunk_cols - 1) / chunk_cols + 1;
+                }
+                if (kind == 0 && sc.go == sc.ge && (long long)m * maxScore + sc.bias >= 255) P.have_t2[cls][strip_height_for(m, 1)] = true;
+                P.maxK = std::max(P.maxK, std::max(K, strip_height_for(m, 0)));
+                P.cig_worst += 2LL * m + 3;
+                P.q_total += m;
+                // rows of the trimmed rectangle = aligned query span <= query length, and a local alignment cannot hold
+                // more inserted query bases than its matches pay for: span <= r * (1 + maxScore / gap_extend)
+                const long long span = std::min<long long>(m, (long long)r * (1 + (maxScore + sc.ge - 1) / std::max(1, (int)sc.ge)) + 1);
+                P.max_rows = std::max<int>(P.max_rows, (int)span);
+            }
         }
-        b->h_mask[p] = mask_len ? mask_len[p] : (m > 30 ? m / 2 : 15);      // ssw_wrap.py:196-199
-        b->max_q = std::max(b->max_q, m);
-        b->max_r = std::max(b->max_r, r);
-        lo = std::min<long long>(lo, std::min(q_off[p], r_off[p]));
-        hi = std::max<long long>(hi, std::max(q_off[p] + m, r_off[p] + r));
-        if (is_tiny_pair(m, r, maxScore, b->sc.bias)) {
-            b->n_tiny += 1;
-            cig_worst += 2LL * m + 3;
-            q_total += m;
-            b->max_rows = std::max<int>(b->max_rows, m);
-        } else if (m > 0 && r > 0) {
-            const int kind = first_pass_kind(m, b->sc.go, b->sc.ge, maxScore, b->sc.bias);
-            const int K = strip_height_for(m, kind);
-            b->have[r > LONG_REF_THRESHOLD ? 1 : 0][kind][K] = true;
-            if (r > LONG_REF_THRESHOLD) {
-                b->long_pairs[kind][K] += 1;
-                b->task_cap[kind][K] += chunk_tasks(m, r, b->chunk_cols, maxScore, b->sc.ge);
+    };
+    int nthreads = 1;
+    if (n >= 262144) nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::vector<Part> parts(nthreads);
+    if (nthreads == 1) scan(0, n, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back(scan, (int32_t)((long long)n * t / nthreads), (int32_t)((long long)n * (t + 1) / nthreads), std::ref(parts[t]));
+        for (auto& x : th) x.join();
+    }
+    for (const Part& P : parts) {
+        if (P.bad >= 0) { set_error("pair " + std::to_string(P.bad) + ": offsets/lengths outside the sequence buffer"); return SSW_ERR_ARG; }
+        for (int c = 0; c < 2; ++c) for (int K = 0; K <= KMAX; ++K) {
+            b->have_t2[c][K] |= P.have_t2[c][K];
+            b->long_pairs[c][K] += P.long_pairs[c][K]; b->task_cap[c][K] += P.task_cap[c][K];
+            for (int k = 0; k < 2; ++k) b->have[c][k][K] |= P.have[c][k][K];
+        }
+        b->n_tiny += P.n_tiny; b->long_total += P.long_total; b->rev_task_total += P.rev_task_total;
+        b->max_q = std::max(b->max_q, P.max_q); b->max_r = std::max(b->max_r, P.max_r);
+        b->max_rows = std::max(b->max_rows, P.max_rows); b->maxK = std::max(b->maxK, P.maxK);
+        cig_worst += P.cig_worst; q_total += P.q_total;
+        lo = std::min(lo, P.lo); hi = std::max(hi, P.hi);
+    }
+    if (b->chunk_cols)                                   // column records of the long references: offsets in pair order
+        for (int32_t p = 0; p < n; ++p) {
+            const int m = q_len[p], r = r_len[p];
+            if (m > 0 && r > LONG_REF_THRESHOLD && !is_tiny_pair(m, r, maxScore, sc.bias)) {
                 h_col_off[p] = col_total;
-                b->long_total += 1;
-                b->rev_task_total += (r + b->chunk_cols - 1) / b->chunk_cols + 1;
                 col_total += ((long long)r + 31) & ~31LL;             // 128-byte aligned: no cache line is shared by two pairs
             }
-            if (kind == 0 && b->sc.go == b->sc.ge && (long long)m * maxScore + b->sc.bias >= 255)
-                b->have_t2[r > LONG_REF_THRESHOLD ? 1 : 0][strip_height_for(m, 1)] = true;
-            b->maxK = std::max(b->maxK, std::max(K, strip_height_for(m, 0)));
-            cig_worst += 2LL * m + 3;
-            q_total += m;
-            // rows of the trimmed rectangle = aligned query span <= query length, and a local alignment cannot hold more
-            // inserted query bases than its matches pay for: span <= r * (1 + maxScore / gap_extend)
-            const long long span = std::min<long long>(m, (long long)r * (1 + (maxScore + b->sc.ge - 1) / std::max(1, (int)b->sc.ge)) + 1);
-            b->max_rows = std::max<int>(b->max_rows, (int)span);
         }
-    }
     if (hi < lo) { lo = 0; hi = 0; }
     if (b->packed) lo &= ~31LL;                          // packed upload: start on a byte (and 16-byte) boundary of the packed buffer
     b->seq_lo = lo; b->seq_hi = hi;
@@ -494,7 +537,7 @@ static int enqueue_cigar_stage(ssw_batch* b, int* launches)
         ta.min_pairs_scale = 16;
         if (const char* e = getenv("SSW_CUDA_TBAND_SEG_SCALE")) ta.min_pairs_scale = atoi(e);
         ta.scratch = b->d_tscr; ta.scratch_stride = 0; ta.dir_bytes = 0;
-        ta.row_pairs_cap = b->tplan.row_pairs_cap; ta.stage_cap = b->tplan.stage_cap;
+        ta.row_pairs_cap = b->tplan.row_pairs_cap; ta.stage_cap = b->tplan.stage_cap; ta.one = 1;
         ta.cigar_buf = b->d_cigar; ta.cigar_cap = b->cigar_cap; ta.cigar_used = b->d_cigar_used;
         int32_t* cnt = b->d_tbins + 2 * TBAND_BINS + 32;
         // the warp-per-pair instances start on the first pass's hand-overs (wide bands, score-0 pairs, thin segments)
@@ -782,10 +825,13 @@ static int fetch_core(ssw_batch* b, ssw_result* out, Reserve reserve, int64_t* c
     if (b->n == 0) return SSW_OK;
     cudaStream_t st = b->stream;
     TraceTimer tt("batch_fetch (total)");
-    b->h_rec.resize(b->n);
+    static_assert(sizeof(PairRec) == sizeof(ssw_result) && offsetof(PairRec, cigar_off) == offsetof(ssw_result, cigar_off) &&
+                  offsetof(PairRec, status) == offsetof(ssw_result, status) && offsetof(PairRec, word) == offsetof(ssw_result, word),
+                  "device records are copied straight into the caller's result array");
+    b->h_rec = reinterpret_cast<PairRec*>(out);
     { TraceTimer t2("  fetch: wait for kernels"); CU_TRY(cudaStreamSynchronize(st)); }
     { TraceTimer t2("  fetch: d2h records");
-    CU_TRY(cudaMemcpyAsync(b->h_rec.data(), b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(b->h_rec, b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st)); }
     const bool cigar_stage = b->sc.flag != 0 && !b->no_cigar;
     if (cigar_stage) {
@@ -808,7 +854,7 @@ static int fetch_core(ssw_batch* b, ssw_result* out, Reserve reserve, int64_t* c
             int launches = 1;
             { const int rc = enqueue_cigar_stage(b, &launches); if (rc != SSW_OK) return rc; }
             b->launches += launches;
-            CU_TRY(cudaMemcpyAsync(b->h_rec.data(), b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(b->h_rec, b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
         }
@@ -822,17 +868,25 @@ static int fetch_core(ssw_batch* b, ssw_result* out, Reserve reserve, int64_t* c
             CU_TRY(cudaStreamSynchronize(st));
         }
     }
-    for (int32_t p = 0; p < b->n; ++p) {
-        const PairRec& r = b->h_rec[p];
-        ssw_result& o = out[p];
-        o.score1 = r.score1; o.score2 = r.score2;
-        o.ref_begin1 = r.ref_begin1; o.ref_end1 = r.ref_end1;
-        o.read_begin1 = r.read_begin1; o.read_end1 = r.read_end1; o.ref_end2 = r.ref_end2;
-        o.cigar_len = r.cigar_len; o.cigar_off = r.cigar_off + cig_base; o.word = r.word;
-        if (r.status & (PS_PUNT | PS_UNSUPPORTED | PS_NEED_GOTOH | PS_BAND_SCRATCH | PS_CIGAR_CAP)) o.status = SSW_PAIR_UNSUPPORTED;
-        else if (r.status & PS_TRACEBACK_ERR) o.status = SSW_PAIR_TRACEBACK_ERR;
-        else o.status = SSW_PAIR_OK;
-        o.status |= r.status << 8;          // internal stage bits, for diagnostics (see ssw_cuda.h)
+    // in place: internal stage bits -> public status, CIGAR offsets -> offsets in the caller's buffer
+    auto convert = [&](int32_t p0, int32_t p1) {
+        for (int32_t p = p0; p < p1; ++p) {
+            ssw_result& o = out[p];
+            const int32_t st_bits = o.status;
+            int32_t pub;
+            if (st_bits & (PS_PUNT | PS_UNSUPPORTED | PS_NEED_GOTOH | PS_BAND_SCRATCH | PS_CIGAR_CAP)) pub = SSW_PAIR_UNSUPPORTED;
+            else if (st_bits & PS_TRACEBACK_ERR) pub = SSW_PAIR_TRACEBACK_ERR;
+            else pub = SSW_PAIR_OK;
+            o.status = pub | (st_bits << 8);          // internal stage bits, for diagnostics (see ssw_cuda.h)
+            o.cigar_off += cig_base;
+        }
+    };
+    if (b->n < 262144) convert(0, b->n);
+    else {
+        const int nt = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(convert, (int32_t)((long long)b->n * t / nt), (int32_t)((long long)b->n * (t + 1) / nt));
+        for (auto& x : th) x.join();
     }
     return SSW_OK;
 }
@@ -956,10 +1010,12 @@ static int align_multi_impl(const int* devices, int n_devices, int32_t n_pairs, 
         if (devices[d] < 0 || devices[d] >= ndev) { set_error("ssw_align_batch_multi: device " + std::to_string(devices[d]) + " does not exist"); return SSW_ERR_NODEVICE; }
     int32_t chunk = 262144;
     if (const char* e = getenv("SSW_CUDA_CHUNK")) { const long v = atol(e); if (v > 0 && v < (1L << 30)) chunk = (int32_t)v; }
-    else if (n_devices > 1) {
-        // enough chunks per device for the shared queue to balance, not so small that a chunk stops filling a GPU
+    else {
+        // about eight chunks per device: enough for the shared queue to balance and for the copies of one chunk to hide
+        // behind the kernels of another; never so small that a chunk stops filling a GPU (mixed batches spread over
+        // many kernel instances), never beyond a million pairs
         const int64_t want = (int64_t)n_pairs / ((int64_t)n_devices * 8);
-        chunk = (int32_t)std::max<int64_t>(65536, std::min<int64_t>(chunk, want));
+        chunk = (int32_t)std::max<int64_t>(n_devices > 1 ? 65536 : 262144, std::min<int64_t>(1 << 20, want));
     }
     int slots = 4;
     if (const char* e = getenv("SSW_CUDA_SLOTS")) { const long v = atol(e); if (v >= 2 && v <= 4) slots = (int)v; }

@@ -177,6 +177,7 @@ struct TbandArgs {
     long long dir_bytes;
     int32_t row_pairs_cap;         // row pairs the direction scratch of one lane holds
     int32_t stage_cap;             // ops
+    int32_t one;                   // the constant 1 as a run-time value (keeps half of the direction-bit adds on the FMA pipe)
     uint32_t* cigar_buf;
     long long cigar_cap;
     unsigned long long* cigar_used;

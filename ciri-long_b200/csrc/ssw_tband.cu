@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
 
     const int go = a.sc.go, ge = a.sc.ge, B = go + ge;
     const unsigned B2 = (unsigned)B * 0x10001u, GO2 = (unsigned)go * 0x10001u, GE2 = (unsigned)ge * 0x10001u;
+    const unsigned one = (unsigned)a.one;                 // 1, but not a compile-time constant (ssw_tband_core.h: tb_max2_*_wins)
 
     for (;;) {
         int base = 0;
@@ -212,20 +213,20 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
             int pos = pos0row;
             int b = 0;
             if (simple && hb == 1) {
-                drow[0] = tb_block<TB_HEAD>(R, 0, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
+                drow[0] = tb_block<TB_HEAD>(R, 0, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, one, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
                 b = 1;
             }
             for (; b < hb; ++b) {
-                drow[b * TB_LANES] = tb_block<TB_ANY>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
+                drow[b * TB_LANES] = tb_block<TB_ANY>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, one, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
             }
             for (; b < tb; ++b) {
-                drow[b * TB_LANES] = tb_block<TB_PLAIN>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
+                drow[b * TB_LANES] = tb_block<TB_PLAIN>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, one, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
             }
             for (; b < NB; ++b) {
-                drow[b * TB_LANES] = tb_block<TB_TAIL>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, maxv2);
+                drow[b * TB_LANES] = tb_block<TB_TAIL>(R, 4 * b, S, ring + pos * TB_LANES, tabS, B2, GO2, GE2, one, maxv2);
                 pos += 4; if (pos >= RING) pos -= RING;
             }
             drow += NB * TB_LANES;

@@ -67,10 +67,12 @@ TB_HD unsigned tb_max2(unsigned a, unsigned b)
 
 // r = max.s16x2(a, b); per half: acc |= IMM if the maximum is NOT a  (a loses strictly:  b > a)
 template <unsigned IMM_LO, unsigned IMM_HI>
-TB_HD unsigned tb_max2_b_wins(unsigned a, unsigned b, unsigned& acc)
+TB_HD unsigned tb_max2_b_wins(unsigned a, unsigned b, unsigned& acc, const unsigned one)
 {
 #if defined(__CUDACC__)
     unsigned r;
+    // (the high half's bit is added as a multiply-add by a register that holds 1: an IMAD on the FMA pipe instead of a
+    // second add on the ALU pipe, which the maxima already keep busy)
     asm("{\n\t.reg .pred pl, ph;\n\t.reg .s16 r0, r1, a0, a1;\n\t"
         "max.s16x2 %0, %2, %3;\n\t"
         "mov.b32 {r0, r1}, %0;\n\t"
@@ -78,11 +80,12 @@ TB_HD unsigned tb_max2_b_wins(unsigned a, unsigned b, unsigned& acc)
         "setp.eq.s16 pl, r0, a0;\n\t"
         "setp.eq.s16 ph, r1, a1;\n\t"
         "@!pl or.b32 %1, %1, %4;\n\t"
-        "@!ph or.b32 %1, %1, %5;\n\t}"
-        : "=&r"(r), "+r"(acc) : "r"(a), "r"(b), "n"(IMM_LO), "n"(IMM_HI));
+        "@!ph mad.lo.u32 %1, %6, %5, %1;\n\t}"
+        : "=&r"(r), "+r"(acc) : "r"(a), "r"(b), "n"(IMM_LO), "n"(IMM_HI), "r"(one));
     return r;
 #else
     const unsigned r = tb_max2(a, b);
+    (void)one;
     if ((r & 0xffff) != (a & 0xffff)) acc |= IMM_LO;
     if ((r >> 16) != (a >> 16)) acc |= IMM_HI;
     return r;
@@ -91,7 +94,7 @@ TB_HD unsigned tb_max2_b_wins(unsigned a, unsigned b, unsigned& acc)
 
 // r = max.s16x2(a, b); per half: acc |= IMM if the maximum IS a  (a >= b)
 template <unsigned IMM_LO, unsigned IMM_HI>
-TB_HD unsigned tb_max2_a_wins(unsigned a, unsigned b, unsigned& acc)
+TB_HD unsigned tb_max2_a_wins(unsigned a, unsigned b, unsigned& acc, const unsigned one)
 {
 #if defined(__CUDACC__)
     unsigned r;
@@ -102,11 +105,12 @@ TB_HD unsigned tb_max2_a_wins(unsigned a, unsigned b, unsigned& acc)
         "setp.eq.s16 pl, r0, a0;\n\t"
         "setp.eq.s16 ph, r1, a1;\n\t"
         "@pl or.b32 %1, %1, %4;\n\t"
-        "@ph or.b32 %1, %1, %5;\n\t}"
-        : "=&r"(r), "+r"(acc) : "r"(a), "r"(b), "n"(IMM_LO), "n"(IMM_HI));
+        "@ph mad.lo.u32 %1, %6, %5, %1;\n\t}"
+        : "=&r"(r), "+r"(acc) : "r"(a), "r"(b), "n"(IMM_LO), "n"(IMM_HI), "r"(one));
     return r;
 #else
     const unsigned r = tb_max2(a, b);
+    (void)one;
     if ((r & 0xffff) == (a & 0xffff)) acc |= IMM_LO;
     if ((r >> 16) == (a >> 16)) acc |= IMM_HI;
     return r;
@@ -181,7 +185,7 @@ TB_HD int tb_row_quirk(int i, int readLen, int refLen, int w)
 enum { TB_PLAIN = 0, TB_ANY = 1, TB_HEAD = 2, TB_TAIL = 3 };
 template <int P, int MODE>
 TB_HD void tb_step(TbRow& R, const int t, unsigned* S, const unsigned char* ringPos, const TbTab tab,
-                   const unsigned B2, const unsigned GO2, const unsigned GE2, unsigned& dirw, unsigned& maxv2)
+                   const unsigned B2, const unsigned GO2, const unsigned GE2, const unsigned one, unsigned& dirw, unsigned& maxv2)
 {
     unsigned w = S[(t + 1) * TB_LANES];
     unsigned Hprev = R.Hl, Eprev = R.Eprev;
@@ -193,16 +197,16 @@ TB_HD void tb_step(TbRow& R, const int t, unsigned* S, const unsigned char* ring
     const unsigned Hup = tb_prmt(w, Hprev, 0x5410u);
     const unsigned Eup = tb_prmt(w, Eprev, 0x5432u);
     const unsigned eopen = Hup - GO2, eext = Eup - GE2;
-    unsigned E = tb_max2_b_wins<1u << (8 * P), 1u << (8 * P + 4)>(eext, eopen, dirw);        // open only if strictly greater
+    unsigned E = tb_max2_b_wins<1u << (8 * P), 1u << (8 * P + 4)>(eext, eopen, dirw, one);        // open only if strictly greater
     const unsigned fopen = R.Hl - GO2, fext = R.Fl - GE2;
-    unsigned F = tb_max2_b_wins<2u << (8 * P), 2u << (8 * P + 4)>(fext, fopen, dirw);
+    unsigned F = tb_max2_b_wins<2u << (8 * P), 2u << (8 * P + 4)>(fext, fopen, dirw, one);
     const unsigned f1 = tb_max2(F, B2);
-    const unsigned gb = tb_max2_a_wins<8u << (8 * P), 8u << (8 * P + 4)>(f1, E, dirw);       // F wins ties against E
+    const unsigned gb = tb_max2_a_wins<8u << (8 * P), 8u << (8 * P + 4)>(f1, E, dirw, one);       // F wins ties against E
     // substitution scores: low row against ref[j], high row against ref[j-1]
     const TbAddr cAddr = tb_tab_addr(tab, (unsigned)ringPos[P * TB_LANES]);
     const unsigned dg = R.Hd + tb_tab_lo(cAddr) + tb_tab_hi(R.cPrevAddr);
     R.cPrevAddr = cAddr;
-    unsigned H = tb_max2_b_wins<4u << (8 * P), 4u << (8 * P + 4)>(dg, gb, dirw);             // diagonal wins ties
+    unsigned H = tb_max2_b_wins<4u << (8 * P), 4u << (8 * P + 4)>(dg, gb, dirw, one);             // diagonal wins ties
     bool hiValid = true;
     if (MODE == TB_ANY || MODE == TB_TAIL) {
         bool loValid;
@@ -227,13 +231,13 @@ TB_HD void tb_step(TbRow& R, const int t, unsigned* S, const unsigned char* ring
 // One block of TB_BLOCK steps; returns the direction word.
 template <int MODE>
 TB_HD unsigned tb_block(TbRow& R, const int t0, unsigned* S, const unsigned char* ringPos, const TbTab tab,
-                        const unsigned B2, const unsigned GO2, const unsigned GE2, unsigned& maxv2)
+                        const unsigned B2, const unsigned GO2, const unsigned GE2, const unsigned one, unsigned& maxv2)
 {
     unsigned dirw = 0;
-    tb_step<0, MODE>(R, t0 + 0, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
-    tb_step<1, MODE>(R, t0 + 1, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
-    tb_step<2, MODE>(R, t0 + 2, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
-    tb_step<3, MODE>(R, t0 + 3, S, ringPos, tab, B2, GO2, GE2, dirw, maxv2);
+    tb_step<0, MODE>(R, t0 + 0, S, ringPos, tab, B2, GO2, GE2, one, dirw, maxv2);
+    tb_step<1, MODE>(R, t0 + 1, S, ringPos, tab, B2, GO2, GE2, one, dirw, maxv2);
+    tb_step<2, MODE>(R, t0 + 2, S, ringPos, tab, B2, GO2, GE2, one, dirw, maxv2);
+    tb_step<3, MODE>(R, t0 + 3, S, ringPos, tab, B2, GO2, GE2, one, dirw, maxv2);
     return dirw;
 }
 

@@ -74,10 +74,10 @@ static void run_warp(std::vector<TbJob>& jobs, const int8_t* mat, int go, int ge
                     if (done[l]) continue;
                     unsigned w;
                     const unsigned char* rp = &ring[(size_t)pos0 * 32 + l];
-                    if (mode == TB_ANY) w = tb_block<TB_ANY>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
-                    else if (mode == TB_HEAD) w = tb_block<TB_HEAD>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
-                    else if (mode == TB_TAIL) w = tb_block<TB_TAIL>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
-                    else w = tb_block<TB_PLAIN>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, maxv2[l]);
+                    if (mode == TB_ANY) w = tb_block<TB_ANY>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, 1u, maxv2[l]);
+                    else if (mode == TB_HEAD) w = tb_block<TB_HEAD>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, 1u, maxv2[l]);
+                    else if (mode == TB_TAIL) w = tb_block<TB_TAIL>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, 1u, maxv2[l]);
+                    else w = tb_block<TB_PLAIN>(R[l], 4 * b, &S[l], rp, &tab[l], B2, GO2, GE2, 1u, maxv2[l]);
                     dirs[((size_t)rho * NB + b) * 32 + l] = w;
                 }
             }
