@@ -115,6 +115,13 @@ struct ssw_batch {
     int32_t *d_idx = nullptr, *d_idx2 = nullptr, *d_idx3 = nullptr, *d_idx4 = nullptr, *d_meta = nullptr;
     // scratch
     unsigned char* d_sscr[2] = {nullptr, nullptr};
+    // the per-list launches of a stage run side by side (FAN streams): every stream has its own class-0 scratch; the
+    // class-1 scratch (megabytes per warp) is cut into two halves instead
+    static constexpr int FAN = 4;
+    unsigned char* d_sscr0x[FAN] = {nullptr, nullptr, nullptr, nullptr};
+    int fan0 = 1, fan1 = 1;
+    cudaStream_t sside[FAN] = {};
+    cudaEvent_t sev[FAN + 1] = {};
     long long sstride[2] = {0, 0}, off_col[2] = {0, 0}, off_bnd[2] = {0, 0}, off_snap[2] = {0, 0};
     int sblocks[2] = {0, 0};
     unsigned char* d_bscr = nullptr;                 // CIGAR pass, narrow instance (bands up to 128 diagonals)
@@ -200,6 +207,10 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     dev_free(b->d_sscr[0], fs); dev_free(b->d_sscr[1], fs); dev_free(b->d_bscr, fs); dev_free(b->d_wscr, fs); dev_free(b->d_cigar, fs); dev_free(b->d_cigar_used, fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+    for (int k = 1; k < ssw_batch::FAN; ++k) dev_free(b->d_sscr0x[k], fs);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto& x : b->sside) if (x) cudaStreamDestroy(x);
+    for (auto& x : b->sev) if (x) cudaEventDestroy(x);
     for (auto& x : b->tside) if (x) cudaStreamDestroy(x);
     for (auto& x : b->tev) if (x) cudaEventDestroy(x);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
@@ -388,7 +399,20 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         blocks = std::max<long long>(1, std::min<long long>(blocks, b->sms));
         blocks = std::min<long long>(blocks, (n + 15) / 16);
         b->sblocks[cls] = (int)blocks;
-        CU_TRY(dev_alloc_t(&b->d_sscr[cls], (size_t)(blocks * SCORE_WARPS * b->sstride[cls]), st));
+        const size_t bytes = (size_t)(blocks * SCORE_WARPS * b->sstride[cls]);
+        CU_TRY(dev_alloc_t(&b->d_sscr[cls], bytes, st));
+        bool fan = n >= 4096;                            // small batches: one stream, nothing to overlap
+        if (const char* e = getenv("SSW_CUDA_FANOUT")) fan = fan && atoi(e) != 0;
+        if (cls == 0 && fan && bytes * ssw_batch::FAN <= (4ULL << 30)) {
+            b->d_sscr0x[0] = b->d_sscr[0];
+            for (int k = 1; k < ssw_batch::FAN; ++k) CU_TRY(dev_alloc_t(&b->d_sscr0x[k], bytes, st));
+            b->fan0 = ssw_batch::FAN;
+        }
+        if (cls == 1 && fan && blocks >= 8) b->fan1 = 2;
+    }
+    if (b->fan0 > 1 || b->fan1 > 1) {
+        for (auto& x : b->sside) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        for (auto& x : b->sev) CU_TRY(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     }
     // CIGAR stage scratch and output
     b->no_cigar = (b->sc.flag & 4) != 0 && b->sc.filterd < 0;              // begin coordinates only: nothing passes ssw.c:850
@@ -606,10 +630,46 @@ extern "C" int ssw_batch_run(ssw_batch* b)
     CU_TRY(cudaMemsetAsync(b->count2(), 0, 4 * N_LISTS * 4, st));
     const size_t nn3 = ((size_t)std::max(b->n, 1) + 16383) & ~(size_t)16383;       // stride of the two hand-over lists in d_idx3
 
+    // The launches of one stage (one per strip-height list) are independent: they go round robin to side streams,
+    // each with scratch of its own, between two events on the batch's stream -- a launch that is down to its last
+    // long tasks shares the machine with the next lists instead of holding it (class 1: a few 16 k-column tasks can
+    // take milliseconds; thin lists of mixed batches likewise).  fan_pick names stream, scratch and grid of a launch.
+    const bool fanning = b->fan0 > 1 || b->fan1 > 1;
+    int fan_rr[2] = {0, 0};
+    cudaStream_t fs = st;
+    unsigned char* fan_scr = nullptr;
+    int fan_blocks = 0;
+    auto fan_begin = [&]() -> int {
+        if (!fanning) return SSW_OK;
+        CU_TRY(cudaEventRecord(b->sev[ssw_batch::FAN], st));
+        for (auto& x : b->sside) CU_TRY(cudaStreamWaitEvent(x, b->sev[ssw_batch::FAN], 0));
+        return SSW_OK;
+    };
+    auto fan_end = [&]() -> int {
+        if (!fanning) return SSW_OK;
+        for (int k = 0; k < ssw_batch::FAN; ++k) {
+            CU_TRY(cudaEventRecord(b->sev[k], b->sside[k]));
+            CU_TRY(cudaStreamWaitEvent(st, b->sev[k], 0));
+        }
+        return SSW_OK;
+    };
+    auto fan_pick = [&](int cls, bool serial) {
+        fs = st; fan_scr = b->d_sscr[cls]; fan_blocks = b->sblocks[cls];
+        if (cls == 0 && b->fan0 > 1) {
+            const int k = serial ? 0 : fan_rr[0]++ % b->fan0;
+            fs = b->sside[k]; fan_scr = b->d_sscr0x[k];
+        } else if (cls == 1 && b->fan1 > 1) {
+            const int k = serial ? 0 : fan_rr[1]++ % b->fan1;
+            fan_blocks = b->sblocks[1] / 2;
+            fs = b->sside[ssw_batch::FAN - 1 - k];                  // (class 0 starts at stream 0, class 1 at the other end)
+            fan_scr = b->d_sscr[1] + (size_t)k * fan_blocks * SCORE_WARPS * b->sstride[1];
+        } else if (fanning) fs = b->sside[0];
+    };
+
     auto score_args = [&](int cls) {
         ScoreArgs a;
         a.b = view; a.sc = b->sc;
-        a.scratch = b->d_sscr[cls]; a.scratch_stride = b->sstride[cls];
+        a.scratch = fan_scr; a.scratch_stride = b->sstride[cls];
         a.off_col = b->off_col[cls]; a.off_bnd = b->off_bnd[cls]; a.off_snap = b->off_snap[cls];
         a.rerun = 0; a.next_idx = nullptr; a.next_base = nullptr; a.next_count = nullptr;
         a.wide_idx = nullptr; a.wide_count = nullptr;
@@ -624,15 +684,15 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         if (!b->chunk_cols || !b->long_pairs[kind][K]) return SSW_OK;
         int32_t* cnt = b->d_task_meta + kind * (KMAX + 1) + K;
         int32_t* cur = b->d_task_meta + 2 * (KMAX + 1) + kind * (KMAX + 1) + K;
-        CU_TRY(cudaMemsetAsync(cnt, 0, 4, st));
-        CU_TRY(cudaMemsetAsync(cur, 0, 4, st));
+        CU_TRY(cudaMemsetAsync(cnt, 0, 4, fs));
+        CU_TRY(cudaMemsetAsync(cur, 0, 4, fs));
         a.ck.chunk_cols = b->chunk_cols; a.ck.max_match = maxScore;
         a.ck.task_pair = b->d_task + b->task_base[kind][K];
         a.ck.task_c0 = b->d_task + b->task_total + b->task_base[kind][K];
         a.ck.task_c1 = b->d_task + 2 * b->task_total + b->task_base[kind][K];
         a.ck.pair_key = b->d_pair_key; a.ck.pair_left = b->d_pair_left;
         a.ck.col_off = b->d_col_off; a.ck.col_pool = b->d_col_pool;
-        CU_TRY(expand_tasks(a.wl, b->long_pairs[kind][K], false, view, b->sc, a.ck, cnt, st, &launches));
+        CU_TRY(expand_tasks(a.wl, b->long_pairs[kind][K], false, view, b->sc, a.ck, cnt, fs, &launches));
         a.wl = WorkList{nullptr, nullptr, cnt, cur};
         return SSW_OK;
     };
@@ -648,49 +708,58 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         CU_TRY(launch_tiny(ta, blocks, st));
         ++launches;
     }
+    { const int rc = fan_begin(); if (rc != SSW_OK) return rc; }
     for (int cls = 0; cls < 2; ++cls)
         for (int kind = 0; kind < 2; ++kind)
             for (int K = 1; K <= KMAX; ++K) {
                 if (!b->have[cls][kind][K]) continue;
                 const int id = list_id(cls, kind, K);
+                fan_pick(cls, false);
                 ScoreArgs a = score_args(cls);
                 a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
                 if (kind == 1) { a.next_idx = b->d_idx2; a.next_base = ls.base + id; a.next_count = b->count2() + id; }
                 else { a.next_idx = b->d_idx4; a.next_base = ls.base + id; a.next_count = b->count3() + id; }   // GOTOH overflow -> TRUNC
                 a.wide_idx = b->d_idx3 + (size_t)kind * nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + kind;
                 if (cls == 1) { const int rc = chunk_launch(a, kind, K); if (rc != SSW_OK) return rc; }
-                CU_TRY(launch_score(K, kind == 1, false, a, b->sblocks[cls], st));
+                CU_TRY(launch_score(K, kind == 1, false, a, fan_blocks, fs));
                 ++launches;
             }
+    { const int rc = fan_end(); if (rc != SSW_OK) return rc; }
     CU_TRY(cudaEventRecord(b->ev[1], st));
+    { const int rc = fan_begin(); if (rc != SSW_OK) return rc; }
     // ---- pairs whose GOTOH-first pass overflowed 8 bits: the truncated-F pass gives their (word) result.
     // strip heights of the two flavours agree for queries of up to 1024 rows, the only ones guessed GOTOH-first
     for (int cls = 0; cls < 2; ++cls)
         for (int K = 1; K <= KMAX; ++K) {
             if (!b->have_t2[cls][K]) continue;
             const int id = list_id(cls, 0, K);
+            fan_pick(cls, false);
             ScoreArgs a = score_args(cls);
             a.wl = WorkList{b->d_idx4, ls.base + id, b->count3() + id, b->cursor3() + id};
             a.rerun = 1;
             a.wide_idx = b->d_idx3 + nn3; a.wide_count = b->count2() + LIST_WIDE32 + 2 + 1;
             if (cls == 1) { const int rc = chunk_launch(a, 0, K); if (rc != SSW_OK) return rc; }      // the GOTOH-first pairs of this K
-            CU_TRY(launch_score(K, true, false, a, b->sblocks[cls], st));
+            CU_TRY(launch_score(K, true, false, a, fan_blocks, fs));
             ++launches;
         }
+    // (the two groups below work on different pairs -- a re-run never re-enters the deciding list -- so they share one fan)
     // ---- deciding byte-flavour pass for pairs whose truncated-F pass stayed below the 8-bit limit
     for (int cls = 0; cls < 2; ++cls)
         for (int K = 1; K <= KMAX; ++K) {
             if (!b->have[cls][1][K]) continue;
             const int id = list_id(cls, 1, K);
+            fan_pick(cls, false);
             ScoreArgs a = score_args(cls);
             a.wl = WorkList{b->d_idx2, ls.base + id, b->count2() + id, b->cursor2() + id};
             a.rerun = 1;
             if (cls == 1) { const int rc = chunk_launch(a, 1, K); if (rc != SSW_OK) return rc; }      // the TRUNC-first pairs of this K
-            CU_TRY(launch_score(K, false, false, a, b->sblocks[cls], st));
+            CU_TRY(launch_score(K, false, false, a, fan_blocks, fs));
             ++launches;
         }
+    { const int rc = fan_end(); if (rc != SSW_OK) return rc; }
     // ---- pairs whose score left the 16-bit comfort zone: 32-bit kernels (rare)
     const int wcls = b->d_sscr[1] ? 1 : 0;
+    fs = st; fan_scr = b->d_sscr[wcls];
     for (int kind = 0; kind < 2 && b->d_sscr[wcls]; ++kind) {            // (no scratch = nothing but tiny pairs in the batch)
         ScoreArgs a = score_args(wcls);
         a.wl = WorkList{b->d_idx3 + (size_t)kind * nn3, nullptr, b->count2() + LIST_WIDE32 + 2 + kind, b->cursor2() + LIST_WIDE32 + 2 + kind};
@@ -702,12 +771,14 @@ extern "C" int ssw_batch_run(ssw_batch* b)
         // ---- reverse pass: strip height follows the read prefix, so any K up to the forward maximum can occur
         CU_TRY(build_lists(1, view, b->sc, LONG_REF_THRESHOLD, ls, st, &launches));
         if (b->chunk_cols) CU_TRY(cudaMemsetAsync(b->count3(), 0, 2 * N_LISTS * 4, st));
+        { const int rc = fan_begin(); if (rc != SSW_OK) return rc; }
         for (int cls = 0; cls < 2; ++cls) {
             if (!b->d_sscr[cls]) continue;
             for (int kind = 0; kind < 2; ++kind) {
                 if (kind == 1 && b->sc.go != b->sc.ge) continue;
                 for (int K = 1; K <= b->maxK; ++K) {
                     const int id = list_id(cls, kind, K);
+                    fan_pick(cls, cls == 1 && b->chunk_cols);          // (long references: the reverse task tables are shared, one list at a time)
                     ScoreArgs a = score_args(cls);
                     a.wl = WorkList{ls.idx, ls.base + id, ls.count + id, ls.cursor + id};
                     if (cls == 1 && b->chunk_cols) {
@@ -715,27 +786,29 @@ extern "C" int ssw_batch_run(ssw_batch* b)
                         // (same partition of d_idx4) and are expanded into column-chunk tasks over the whole prefix
                         a.ck.chunk_cols = b->chunk_cols; a.ck.max_match = maxScore;
                         a.next_idx = b->d_idx4; a.next_base = ls.base + id; a.next_count = b->count3() + id;
-                        CU_TRY(launch_score(K, kind == 1, true, a, b->sblocks[cls], st));
+                        CU_TRY(launch_score(K, kind == 1, true, a, fan_blocks, fs));
                         int32_t* cnt = b->d_task_meta + kind * (KMAX + 1) + K;
                         int32_t* cur = b->d_task_meta + 2 * (KMAX + 1) + kind * (KMAX + 1) + K;
-                        CU_TRY(cudaMemsetAsync(cnt, 0, 4, st));
-                        CU_TRY(cudaMemsetAsync(cur, 0, 4, st));
+                        CU_TRY(cudaMemsetAsync(cnt, 0, 4, fs));
+                        CU_TRY(cudaMemsetAsync(cur, 0, 4, fs));
                         ScoreArgs t = a;
                         t.ck.task_pair = b->d_rtask; t.ck.task_c0 = b->d_rtask + b->rev_task_total;
                         t.ck.task_c1 = b->d_rtask + 2 * b->rev_task_total; t.ck.task_res = b->d_rres;
                         t.ck.pair_key = b->d_pair_key; t.ck.pair_left = b->d_pair_left;
                         const WorkList longList{b->d_idx4, ls.base + id, b->count3() + id, nullptr};
-                        CU_TRY(expand_tasks(longList, b->long_total, true, view, b->sc, t.ck, cnt, st, &launches));
+                        CU_TRY(expand_tasks(longList, b->long_total, true, view, b->sc, t.ck, cnt, fs, &launches));
                         t.wl = WorkList{nullptr, nullptr, cnt, cur};
-                        CU_TRY(launch_score(K, kind == 1, true, t, b->sblocks[cls], st));
+                        CU_TRY(launch_score(K, kind == 1, true, t, fan_blocks, fs));
                         launches += 2;
                         continue;
                     }
-                    CU_TRY(launch_score(K, kind == 1, true, a, b->sblocks[cls], st));
+                    CU_TRY(launch_score(K, kind == 1, true, a, fan_blocks, fs));
                     ++launches;
                 }
             }
         }
+        { const int rc = fan_end(); if (rc != SSW_OK) return rc; }
+        fs = st; fan_scr = b->d_sscr[wcls];
         for (int kind = 0; kind < 2 && b->d_sscr[wcls]; ++kind) {
             const int id = LIST_WIDE32 + kind;
             ScoreArgs a = score_args(wcls);

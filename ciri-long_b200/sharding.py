@@ -31,12 +31,30 @@ def lpt_shards(q_len, r_len, n_shards):
     return [np.sort(order[owner == s]) for s in range(n_shards)]
 
 
-def shard_batch(batch, rank, world):
-    """The sub-batch rank `rank` of `world` aligns, plus its original indices (views into the same
-    code buffer: offsets are explicit in the C ABI, so no sequence bytes are moved)."""
+def shard_batch(batch, rank, world, compact=True):
+    """The sub-batch rank `rank` of `world` aligns, plus its original indices.
+
+    compact=True (default) copies the shard's sequences into a buffer of its own, pair-major ([q0 r0 q1 r1 ...]), and
+    rebases the offsets: the library uploads the byte range a batch references, so a shard that kept the full buffer
+    with strided pair indices would send (nearly) the whole buffer to every GPU.  compact=False returns views into the
+    caller's buffer (offsets unchanged), for shards that are already contiguous."""
     idx = lpt_shards(batch.q_len, batch.r_len, world)[rank]
-    return idx, dict(seqs=batch.seqs, q_off=batch.q_off[idx], q_len=batch.q_len[idx],
-                     r_off=batch.r_off[idx], r_len=batch.r_len[idx])
+    if not compact:
+        return idx, dict(seqs=batch.seqs, q_off=batch.q_off[idx], q_len=batch.q_len[idx],
+                         r_off=batch.r_off[idx], r_len=batch.r_len[idx])
+    ql, rl = batch.q_len[idx].astype(np.int64), batch.r_len[idx].astype(np.int64)
+    lens = np.stack([ql, rl], 1).reshape(-1)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    q_off, r_off = offs[0:-1:2].copy(), offs[1::2].copy()
+    seqs = np.empty(int(offs[-1]), dtype=batch.seqs.dtype)
+
+    def ragged(starts, n):
+        total = int(n.sum())
+        seg = np.cumsum(n) - n
+        return np.repeat(starts.astype(np.int64) - seg, n) + np.arange(total, dtype=np.int64)
+    seqs[ragged(q_off, ql)] = batch.seqs[ragged(batch.q_off[idx], ql)]
+    seqs[ragged(r_off, rl)] = batch.seqs[ragged(batch.r_off[idx], rl)]
+    return idx, dict(seqs=seqs, q_off=q_off, q_len=batch.q_len[idx].copy(), r_off=r_off, r_len=batch.r_len[idx].copy())
 
 
 def gather_results(n_pairs, parts):

@@ -64,3 +64,20 @@ def test_gloo_world2_gather():
     for p in procs:
         p.join(timeout=60)
     assert ok
+
+
+def test_shard_batch_compacts_its_sequences():
+    """a shard carries only its own bytes (pair-major, rebased offsets) and the same sequences as the original pairs"""
+    import ciri_long_b200  # noqa: F401
+    from ciri_long_b200 import sharding, workloads as W
+    b = W.concat_batches([W.junction_pairs(600, seed=3), W.square_pairs(40, 200, params=(10, 4, 8, 2))], shuffle_seed=1)
+    tot = 0
+    for rank in range(4):
+        idx, sub = sharding.shard_batch(b, rank, 4)
+        assert len(sub["seqs"]) == int(b.q_len[idx].sum() + b.r_len[idx].sum())
+        tot += len(sub["seqs"])
+        for k in (0, len(idx) // 2, len(idx) - 1):
+            i = idx[k]
+            assert (sub["seqs"][sub["q_off"][k]:sub["q_off"][k] + sub["q_len"][k]] == b.query(i)).all()
+            assert (sub["seqs"][sub["r_off"][k]:sub["r_off"][k] + sub["r_len"][k]] == b.ref(i)).all()
+    assert tot == int(b.q_len.sum() + b.r_len.sum())
