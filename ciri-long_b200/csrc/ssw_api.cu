@@ -847,8 +847,13 @@ static int rerun_big_bands(ssw_batch* b, std::vector<int32_t>& big)
     long long need = 0;
     for (int32_t p : big) {
         const PairRec& r = b->h_rec[p];
-        const long long readLen = r.read_end1 - r.read_begin1 + 1;
-        need = std::max(need, (4 * readLen + 1) * readLen + (4 * readLen + 8) * 8 + 64);
+        // the widest band the doubling loop can reach: it starts at |refLen - readLen| + 1, whatever that is, and goes on
+        // while the band is below 2 * readLen (ssw.c:571-632)
+        const long long readLen = r.read_end1 - r.read_begin1 + 1, refLen = r.ref_end1 - r.ref_begin1 + 1;
+        const long long bw0 = std::llabs(refLen - readLen) + 1;
+        const long long bwMax = std::max(bw0, 2 * readLen);
+        const long long rowStride = (2 * bwMax + 1 + 15) & ~15LL;
+        need = std::max(need, rowStride * readLen + (2 * bwMax + 4) * 8 + 80);
     }
     const long long stride = ((long long)b->bstage * 4 + need + 255) & ~255LL;
     long long warps = std::max<long long>(1, std::min<long long>((6LL << 30) / stride, (long long)big.size()));
@@ -907,11 +912,6 @@ static int fetch_core(ssw_batch* b, ssw_result* out, Reserve reserve, int64_t* c
     CU_TRY(cudaMemcpyAsync(b->h_rec, b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st)); }
     const bool cigar_stage = b->sc.flag != 0 && !b->no_cigar;
-    if (cigar_stage) {
-        std::vector<int32_t> big;
-        for (int32_t p = 0; p < b->n; ++p) if (b->h_rec[p].status & PS_BAND_SCRATCH) big.push_back(p);
-        if (!big.empty()) { const int rc = rerun_big_bands(b, big); if (rc != SSW_OK) return rc; }
-    }
     unsigned long long used = 0;
     int64_t cig_base = 0;
     if (cigar_stage) {
@@ -923,14 +923,19 @@ static int fetch_core(ssw_batch* b, ssw_result* out, Reserve reserve, int64_t* c
             b->d_cigar = nullptr;
             b->cigar_cap = b->cigar_worst;
             CU_TRY(dev_alloc_t(&b->d_cigar, (size_t)b->cigar_cap, st));
-            CU_TRY(clear_status_bits(b->view(), PS_CIGAR_CAP, st));
+            CU_TRY(clear_status_bits(b->view(), PS_CIGAR_CAP | PS_BAND_SCRATCH, st));
             int launches = 1;
             { const int rc = enqueue_cigar_stage(b, &launches); if (rc != SSW_OK) return rc; }
             b->launches += launches;
             CU_TRY(cudaMemcpyAsync(b->h_rec, b->d_rec, (size_t)b->n * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
         }
+        // pairs whose direction matrix did not fit the per-warp scratch (after a possible regrow, which repeats the stage)
+        std::vector<int32_t> big;
+        for (int32_t p = 0; p < b->n; ++p) if (b->h_rec[p].status & PS_BAND_SCRATCH) big.push_back(p);
+        if (!big.empty()) { const int rc = rerun_big_bands(b, big); if (rc != SSW_OK) return rc; }
+        CU_TRY(cudaMemcpyAsync(&used, b->d_cigar_used, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
         if (cigar_used) *cigar_used = (int64_t)used;
         if ((long long)used > b->cigar_cap) { set_error("internal cigar buffer exhausted"); return SSW_ERR_CIGAR_CAP; }
         if (used > 0) {
