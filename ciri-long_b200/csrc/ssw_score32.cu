@@ -4,7 +4,8 @@
 // as its score comes near the range where the reference's own arithmetic starts to matter: the word
 // flavour saturates at 32767 (`_mm_adds_epi16`, ssw.c:442), and the truncated-F gate of the packed
 // kernel needs scores below 16000.  Such pairs (e.g. >3.3 kb near-perfect matches at match = 10) are
-// re-done here with one strip per lane in plain int32 registers and the saturating add made explicit:
+// re-done here with one strip per lane in int32 registers (32-bit DPX: VIADDMNMX / VIMNMX3) and the saturating add
+// made explicit:
 //     H = max(0, min(Hdiag + s, 32767), E, F)
 // Same wavefront, same strip layouts (right-aligned strips for GOTOH, segment-aligned strips with
 // arbitrary live counts for TRUNC), same outputs; throughput is secondary (a handful of pairs).
@@ -18,7 +19,7 @@ constexpr int K32 = 16;          // rows per strip
 constexpr int V32 = 32;          // strips per tile (one per lane)
 
 template <bool TRUNC, bool REV>
-__device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* ws)
+__device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* ws, const int* matS)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = lane_id();
@@ -69,16 +70,18 @@ __device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* 
                 first = l * segLen + g * base + (g < extra ? g : extra);
                 segStart = valid && g == 0 && l >= 1;
             }
-            int qc[K32], E[K32], Hd[K32], snapH[K32];
+            // (the first row that holds a column's maximum is tracked with the maximum itself, so the best cell needs no
+            // snapshot of the strip's column: ssw.c:299-308 asks for the smallest row with H == max in the best column)
+            int qc[K32], E[K32], Hd[K32];
 #pragma unroll
             for (int i = 0; i < K32; ++i) {
                 const int r = first + i;
                 int c = 4;
                 if (r >= 0 && r < m && i < live) { c = qb[(long long)r * qs]; if ((unsigned)c > 4u) c = 4; }
-                qc[i] = c; E[i] = 0; Hd[i] = 0; snapH[i] = 0;
+                qc[i] = c; E[i] = 0; Hd[i] = 0;
             }
             const int wv = (TRUNC && lastTile) ? Vtot - 1 - p * V32 : V32 - 1;
-            int Hout = 0, Fout = 0, R = 0, diagIn = 0, best = 0, bcol = -1, termflag = 0;
+            int Hout = 0, Fout = 0, R = 0, diagIn = 0, best = 0, bcol = -1, brow = 0, termflag = 0;
             const int steps = n + wv;
             for (int s = 0; s < steps; ++s) {
                 int rH = __shfl_up_sync(FULL, Hout, 1), rF = __shfl_up_sync(FULL, Fout, 1), rR = __shfl_up_sync(FULL, R, 1);
@@ -93,28 +96,26 @@ __device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* 
                 const bool colOk = (unsigned)c < (unsigned)n;
                 int rc = 4;
                 if (colOk) { rc = rb[(long long)c * rs]; if ((unsigned)rc > 4u) rc = 4; }
+                const int* mrow = matS + rc * 5;                            // (N row / column of the matrix are zero: scoring_supported)
                 int diag = diagIn; diagIn = rH;
-                int F = rF, mx = 0, Hk = rH, Fk = rF;
+                int F = rF, mx = 0, mrowIdx = 0, Hk = rH, Fk = rF;
 #pragma unroll
                 for (int i = 0; i < K32; ++i) {
                     if (i < live) {
-                        const int sc = (rc == 4 || qc[i] == 4) ? 0 : a.sc.mat[rc * 5 + qc[i]];
-                        int x = diag + sc;
-                        if (x > 32767) x = 32767;                          // _mm_adds_epi16 (ssw.c:442)
-                        if (E[i] > x) x = E[i];
-                        int h = x > F ? x : F; if (h < 0) h = 0;
+                        const int x = __viaddmin_s32(diag, mrow[qc[i]], 32767);          // _mm_adds_epi16 (ssw.c:442)
+                        const int h = __vimax3_s32_relu(x, E[i], F);
                         int u;
                         if (TRUNC && i == 0 && segStart) {                 // cut vertical-gap chain (ssw.c:467-478)
-                            const int h0 = x > 0 ? x : 0;
+                            const int h0 = __vimax_s32_relu(x, E[i]);
                             u = h0 - go;
                             F = u;
                         } else {
                             u = h - go;
-                            F = F - ge > u ? F - ge : u;
+                            F = __viaddmax_s32(F, -ge, u);
                         }
-                        E[i] = E[i] - ge > u ? E[i] - ge : u;
+                        E[i] = __viaddmax_s32(E[i], -ge, u);
                         diag = Hd[i]; Hd[i] = h;
-                        if (h > mx) mx = h;
+                        if (h > mx) { mx = h; mrowIdx = i; }
                         if (i == live - 1) { Hk = h; Fk = F; }
                     }
                 }
@@ -122,11 +123,7 @@ __device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* 
                 if (!colOk || !valid) mx = 0;
                 R = rR > mx ? rR : mx;
                 if (REV && !exactMode && mx > terminate) { overCol = c < overCol ? c : overCol; mx = 0; }
-                if (mx > best) {
-                    best = mx; bcol = c;
-#pragma unroll
-                    for (int i = 0; i < K32; ++i) snapH[i] = Hd[i];
-                }
+                if (mx > best) { best = mx; bcol = c; brow = first + mrowIdx; }
                 if (lane == wv && colOk) {
                     if (!lastTile) bnd[c] = make_uint2((unsigned)(Hout & 0xffff) | ((unsigned)(Fout & 0xffff) << 16), (unsigned)R);
                     else if (!REV) colbuf[c] = (unsigned)R | ((unsigned)Hout << 16);
@@ -139,12 +136,7 @@ __device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* 
             if (M > 0) {
                 const int col = __reduce_min_sync(FULL, best == M ? bcol : 0x7fffffff);
                 const int owner = __reduce_min_sync(FULL, (best == M && bcol == col) ? lane : 1000);
-                int row = 0;
-                if (lane == owner) {
-#pragma unroll
-                    for (int i = K32 - 1; i >= 0; --i) if (i < live && snapH[i] == M) row = first + i;
-                    if (row > m - 1) row = m - 1;
-                }
+                int row = brow > m - 1 ? m - 1 : brow;
                 row = __shfl_sync(FULL, row, owner);
                 if (M > candM || (M == candM && col < candCol)) { candM = M; candCol = col; candRow = row; }
             }
@@ -193,8 +185,11 @@ __device__ void score32_pair(const ScoreArgs& a, const int pair, unsigned char* 
 template <bool TRUNC, bool REV>
 __global__ void __launch_bounds__(SCORE32_WARPS * 32) score32_kernel(const ScoreArgs a)
 {
+    __shared__ int matS[25];
     const int count = *a.wl.count;
     if (count <= 0) return;
+    if (threadIdx.x < 25) matS[threadIdx.x] = a.sc.mat[threadIdx.x];
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int base = a.wl.base ? *a.wl.base : 0;
     unsigned char* ws = a.scratch + (size_t)(blockIdx.x * SCORE32_WARPS + warp) * a.scratch_stride;
@@ -203,7 +198,7 @@ __global__ void __launch_bounds__(SCORE32_WARPS * 32) score32_kernel(const Score
         if (lane_id() == 0) idx = atomicAdd(a.wl.cursor, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        score32_pair<TRUNC, REV>(a, a.wl.idx[base + idx], ws);
+        score32_pair<TRUNC, REV>(a, a.wl.idx[base + idx], ws, matS);
         __syncwarp();
     }
 }

@@ -204,3 +204,23 @@ def test_multi_device_call_matches_single_device(sw, monkeypatch):
     for i in range(0, len(b), 7):
         assert (c1[r1["cigar_off"][i]:r1["cigar_off"][i] + r1["cigar_len"][i]] == c2[r2["cigar_off"][i]:r2["cigar_off"][i] + r2["cigar_len"][i]]).all()
     assert len(c1) == len(c2) == int(r1["cigar_len"].sum())
+
+
+@pytest.mark.parametrize("lane_kernel", [False, True])
+def test_band_wider_than_the_scratch_is_rerun(sw, oracle, monkeypatch, lane_kernel):
+    """a 700-900-nt deletion joined by two strong flanks (10/4/8/2 pays for it): the first band is already ~1700
+    diagonals wide, the direction matrix does not fit the per-warp scratch and the pair is re-run from
+    ssw_batch_fetch with a scratch sized for it -- same CIGAR as the reference's single malloc'ed matrix"""
+    from ciri_long_b200 import workloads as W
+    monkeypatch.setenv("SSW_CUDA_TBAND_MIN", "0" if lane_kernel else "1000000000")
+    rng = np.random.default_rng(51)
+    qs, rs = [], []
+    for k in range(6):
+        a, c = rng.integers(0, 4, 320).astype(np.int8), rng.integers(0, 4, 320).astype(np.int8)
+        junk = rng.integers(0, 4, int(rng.integers(700, 900))).astype(np.int8)
+        read, ref = np.concatenate([a, c]), np.concatenate([a, junk, c])
+        if k % 2:
+            read, ref = ref, read                                  # the same as a long insertion
+        qs.append(read); rs.append(ref)
+    rec, exp = compare_all(sw, oracle, W.from_lists(qs, rs, (10, 4, 8, 2), name="huge-gap"))
+    assert (exp["band_width"] > 512).any()
