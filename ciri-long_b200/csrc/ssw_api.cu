@@ -120,7 +120,7 @@ struct ssw_batch {
     static constexpr int FAN = 4;
     unsigned char* d_sscr0x[FAN] = {nullptr, nullptr, nullptr, nullptr};
     int fan0 = 1, fan1 = 1;
-    cudaStream_t sside[FAN] = {};
+    cudaStream_t sside[FAN] = {};                    // (aliases of the first FAN entries of tside: the device has few hardware queues)
     cudaEvent_t sev[FAN + 1] = {};
     long long sstride[2] = {0, 0}, off_col[2] = {0, 0}, off_bnd[2] = {0, 0}, off_snap[2] = {0, 0};
     int sblocks[2] = {0, 0};
@@ -209,7 +209,6 @@ extern "C" void ssw_batch_destroy(ssw_batch* b)
     for (int k = 0; k < 5; ++k) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
     for (int k = 1; k < ssw_batch::FAN; ++k) dev_free(b->d_sscr0x[k], fs);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    for (auto& x : b->sside) if (x) cudaStreamDestroy(x);
     for (auto& x : b->sev) if (x) cudaEventDestroy(x);
     for (auto& x : b->tside) if (x) cudaStreamDestroy(x);
     for (auto& x : b->tev) if (x) cudaEventDestroy(x);
@@ -401,17 +400,24 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
         b->sblocks[cls] = (int)blocks;
         const size_t bytes = (size_t)(blocks * SCORE_WARPS * b->sstride[cls]);
         CU_TRY(dev_alloc_t(&b->d_sscr[cls], bytes, st));
-        bool fan = n >= 4096;                            // small batches: one stream, nothing to overlap
-        if (const char* e = getenv("SSW_CUDA_FANOUT")) fan = fan && atoi(e) != 0;
-        if (cls == 0 && fan && bytes * ssw_batch::FAN <= (4ULL << 30)) {
+        // SSW_CUDA_FANOUT: 0 = off, 1 (default) = long references only, 2 = short references as well.  Measured: long
+        // references (S1) 489 -> 402 ms per step; short ones gain 1-3 % in the score stages of C2 / C5 but the CIGAR
+        // stage that follows ran 5-8 % slower on mixed batches for reasons not understood, so they stay on one stream.
+        int fan_mode = n >= 4096 ? 1 : 0;                // small batches: one stream, nothing to overlap
+        if (const char* e = getenv("SSW_CUDA_FANOUT")) fan_mode = std::min(fan_mode == 0 ? 0 : 2, atoi(e));
+        const bool fan = fan_mode >= 1;
+        if (cls == 0 && fan_mode >= 2 && bytes * ssw_batch::FAN <= (4ULL << 30)) {
             b->d_sscr0x[0] = b->d_sscr[0];
             for (int k = 1; k < ssw_batch::FAN; ++k) CU_TRY(dev_alloc_t(&b->d_sscr0x[k], bytes, st));
             b->fan0 = ssw_batch::FAN;
         }
         if (cls == 1 && fan && blocks >= 8) b->fan1 = 2;
     }
+    // One set of side streams serves the score stages (first FAN of them) and the CIGAR stage (all): streams beyond
+    // the device's hardware queues (8 by default) would share queues and serialise what is meant to overlap.
     if (b->fan0 > 1 || b->fan1 > 1) {
-        for (auto& x : b->sside) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        for (auto& x : b->tside) if (!x) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        for (int k = 0; k < ssw_batch::FAN; ++k) b->sside[k] = b->tside[k];
         for (auto& x : b->sev) CU_TRY(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     }
     // CIGAR stage scratch and output
@@ -429,7 +435,7 @@ static int batch_alloc(ssw_batch* b, const int8_t* seqs, int64_t seqs_len, const
             if (const char* e = getenv("SSW_CUDA_TBAND_BUDGET_MB")) { const long v = atol(e); if (v > 0) budget = (long long)v << 20; }
             CU_TRY(tband_plan(b->device, b->sms, b->max_rows, budget, &b->tplan));
             CU_TRY(tband_configure());
-            for (auto& x : b->tside) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+            for (auto& x : b->tside) if (!x) CU_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
             for (auto& x : b->tev) CU_TRY(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
             CU_TRY(dev_alloc_t(&b->d_tscr, (size_t)b->tplan.scratch_bytes, st));
             CU_TRY(dev_alloc_t(&b->d_tlists, 4 * nn, st));
