@@ -455,3 +455,25 @@ def test_mixed_length_batch(sw, oracle):
                          shuffle_seed=45)
     rng = np.random.default_rng(46)
     check_batch(sw, oracle, b, sample=rng.choice(len(b), 500, replace=False))
+
+
+def test_clip_vs_400kb_windows(sw, oracle):
+    """S1 as it really is (find_bsj.py:191-215): clipped ends of 20-600 nt against 400-600 kb genomic windows that
+    are views into one genome buffer (column-chunk tasks, bounded reverse look, fan-out of the per-list launches)"""
+    import torch
+    from ciri_long_b200 import workloads as W
+    b = W.clip_window_pairs_torch(10, torch.device("cpu"), seed=61, genome_len=1 << 21, win_min=400000, win_max=600000)
+    assert b.r_len.min() >= 400000
+    check_batch(sw, oracle, b)
+    rec, _ = run_batch(sw, b, flag=0)
+    assert ((rec["status"] & 0xff) == 0).all()
+
+
+@pytest.mark.parametrize("params", [(1, 1, 1, 1), (2, 2, 3, 1)])
+def test_square_4096(sw, oracle, params):
+    """C4's largest row at the find_bsj scoring too (four tiles of 1024 rows; 10/4/8/2 is covered by test_square_sweep
+    up to 2048 and by test_scores_beyond_16_bit_comfort at 4096)"""
+    from ciri_long_b200 import workloads as W
+    b = W.square_pairs(3, 4096, params=params)
+    check_batch(sw, oracle, b)
+    check_batch(sw, oracle, b, flag=0)
