@@ -294,7 +294,7 @@ def run_reference(args, rank, world):
                                  "sample": "%d pairs of the workload per step (same recipe, numpy stream), unmodified reference libssw.so "
                                            "via ctypes on pre-encoded int8 arrays, Pool(%d, spawn) x chunks of 250, flag=1" % (len(sample), arm.cores)},
                 "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(out))
+    emit(out)
 
 
 def c4_rows(args):
@@ -330,7 +330,7 @@ def run_reference_c4(args):
                 "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": kind,
                                  "sample": "per row 256-32768 pairs of the row's recipe, reference libssw.so via ctypes, Pool(%d) x chunks of 250" % cores},
                 "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -557,7 +557,7 @@ def run_ours(args, rank, world, local_rank):
         out["parity"] = parity
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -647,10 +647,28 @@ def run_ours_c4(args, sw, torch, dev, local_rank):
     if cpu_s > 0:
         out["cpu_baseline"] = {"value": cpu_cells / cpu_s / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
                                "sample": "per row the first 256-32768 pairs of the GPU's own batch, full mode; per-row figures in `sweep`"}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the real stdout (everything else -- NCCL's version banner, library
+    chatter -- goes to stderr, see main)"""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line.encode())
 
 
 def main():
+    global _REAL_STDOUT
+    # keep stdout for the JSON line alone: C libraries (NCCL prints its version there) write to fd 1 directly
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
