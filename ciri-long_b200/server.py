@@ -158,7 +158,10 @@ class AlignClient(object):
         blob = "".join([x for pair in zip(queries, refs) for x in pair]).encode("latin-1", "replace")
         buf[8 * n:8 * n + len(blob)] = blob
         self.service.req_q.put((self.slot, n) + tuple(params) + (bool(need_cigar),))
-        ans = self.resp_q.get()
+        try:
+            ans = self.resp_q.get(timeout=self.service.timeout_s)
+        except Exception:
+            raise RuntimeError("align service: no answer within %.0f s (owner process gone?)" % self.service.timeout_s)
         if ans[0] != "ok":
             raise RuntimeError("align service: " + str(ans[1]))
         _, n_back, n_ops = ans
@@ -204,8 +207,9 @@ class AlignService(object):
     """Owner processes (one per device) + ``n_clients`` client slots.  Create it in the parent BEFORE the worker
     pool; forked workers call ``attach()`` (or ``client()``) once to claim a slot."""
 
-    def __init__(self, devices=(0,), n_clients=None, arena_mb=64, max_pairs=262144, flush_ms=2.0, backend="cuda"):
+    def __init__(self, devices=(0,), n_clients=None, arena_mb=64, max_pairs=262144, flush_ms=2.0, backend="cuda", timeout_s=600.0):
         ctx = mp.get_context("spawn")                      # the owners are spawned: no CUDA state is ever forked
+        self.timeout_s = float(timeout_s)                  # a client gives up (with an error) if no answer comes back
         self.n_clients = n_clients or (os.cpu_count() or 1)
         self.arena_bytes = int(arena_mb) << 20
         self.req_q = ctx.Queue()
