@@ -65,20 +65,27 @@ __device__ __forceinline__ void tb_hand_over(const TbandArgs& a, PairRec* rec, i
 __global__ void tband_key_kernel(TbandArgs a, int pass, const int32_t* in_idx, const int32_t* in_count)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= *in_count) return;
-    const int pair = in_idx[k];
-    PairRec* rec = a.b.rec + pair;
-    int bw, readLen, refLen;
-    if (!tb_geometry(a, rec, pass, bw, readLen, refLen)) {
-        if (pass == 0) { int w = 1; if (rec->ref_begin1 >= 0) { w = rec->ref_end1 - rec->ref_begin1 - (rec->read_end1 - rec->read_begin1); if (w < 0) w = -w; w += 1; } tb_hand_over(a, rec, pair, w, 0); }
-        else tb_hand_over(a, rec, pair, -rec->cigar_len, (int)rec->cigar_off);
-        a.keys[k] = -1;
-        return;
+    int bin = -1;
+    if (k < *in_count) {
+        const int pair = in_idx[k];
+        PairRec* rec = a.b.rec + pair;
+        int bw, readLen, refLen;
+        if (!tb_geometry(a, rec, pass, bw, readLen, refLen)) {
+            if (pass == 0) { int w = 1; if (rec->ref_begin1 >= 0) { w = rec->ref_end1 - rec->ref_begin1 - (rec->read_end1 - rec->read_begin1); if (w < 0) w = -w; w += 1; } tb_hand_over(a, rec, pair, w, 0); }
+            else tb_hand_over(a, rec, pair, -rec->cigar_len, (int)rec->cigar_off);
+        } else {
+            if (pass == 0) { rec->cigar_len = -bw; rec->cigar_off = 0; }
+            bin = tb_bin(tb_blocks(bw), (readLen + 1) / 2);
+        }
+        a.keys[k] = bin;
     }
-    if (pass == 0) { rec->cigar_len = -bw; rec->cigar_off = 0; }
-    const int bin = tb_bin(tb_blocks(bw), (readLen + 1) / 2);
-    a.keys[k] = bin;
-    atomicAdd(a.bin_count + bin, 1);
+    // one atomic per distinct bin and warp: batches of alike pairs (millions of junction pairs in a handful of bins)
+    // would otherwise serialise on a few counters
+    const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
+    if (bin >= 0) {
+        const unsigned peers = __match_any_sync(act, bin);
+        if ((int)(__ffs(peers) - 1) == lane_id()) atomicAdd(a.bin_count + bin, __popc(peers));
+    }
 }
 
 // one CTA: exclusive prefix sums over the bins (bin order = processing order), per-instance segments
@@ -118,16 +125,25 @@ __global__ void tband_scan_kernel(TbandArgs a)
 __global__ void tband_scatter_kernel(TbandArgs a, const int32_t* in_idx, const int32_t* in_count)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= *in_count) return;
-    const int bin = a.keys[k];
-    if (bin < 0) return;
-    const int pair = in_idx[k];
-    if (a.seg[24 + tb_instance_of(TB_NB_MAX - bin / (TB_RB_MAX + 1))]) {        // too few pairs for a launch of that instance
-        PairRec* rec = a.b.rec + pair;
-        tb_hand_over(a, rec, pair, -rec->cigar_len, (int)rec->cigar_off);
-        return;
+    int bin = -1, pair = 0;
+    if (k < *in_count) {
+        bin = a.keys[k];
+        pair = in_idx[k];
+        if (bin >= 0 && a.seg[24 + tb_instance_of(TB_NB_MAX - bin / (TB_RB_MAX + 1))]) {        // too few pairs for a launch of that instance
+            PairRec* rec = a.b.rec + pair;
+            tb_hand_over(a, rec, pair, -rec->cigar_len, (int)rec->cigar_off);
+            bin = -1;
+        }
     }
-    a.sorted[a.bin_base[bin] + atomicAdd(a.bin_count + bin, 1)] = pair;
+    const unsigned act = __ballot_sync(0xffffffffu, bin >= 0);
+    if (bin >= 0) {
+        const unsigned peers = __match_any_sync(act, bin);
+        const int leader = __ffs(peers) - 1;
+        int pos = 0;
+        if (lane_id() == leader) pos = atomicAdd(a.bin_count + bin, __popc(peers));
+        pos = __shfl_sync(peers, pos, leader);
+        a.sorted[a.bin_base[bin] + pos + __popc(peers & ((1u << lane_id()) - 1u))] = pair;
+    }
 }
 
 __global__ void tband_reset_kernel(TbandArgs a, int32_t* count_to_clear)
@@ -257,11 +273,20 @@ __global__ void __launch_bounds__(TBAND_WARPS * 32) tband_kernel(const TbandArgs
         if (lane == 31 && total > 0) wbase = (long long)atomicAdd(a.cigar_used, (unsigned long long)total);
         wbase = __shfl_sync(FULL, wbase, 31);
         const long long off = wbase + incl - nOps;
+        // pairs whose band doubles: next pass's list, one atomic per warp
+        const int bw2 = 2 * J.bw;
+        const bool toNext = have && again && !(tb_steps(bw2) > TB_MAX_STEPS || pass + 1 >= TB_PASSES);
+        const unsigned nextMask = __ballot_sync(FULL, toNext);
+        if (nextMask) {
+            int nbase = 0;
+            const int leader = __ffs(nextMask) - 1;
+            if (lane == leader) nbase = atomicAdd(a.next_count, __popc(nextMask));
+            nbase = __shfl_sync(FULL, nbase, leader);
+            if (toNext) { rec->cigar_len = -bw2; rec->cigar_off = mx; a.next_idx[nbase + __popc(nextMask & ((1u << lane) - 1u))] = pair; }
+        }
         if (have) {
             if (again) {
-                const int bw2 = 2 * J.bw;
-                if (tb_steps(bw2) > TB_MAX_STEPS || pass + 1 >= TB_PASSES) tb_hand_over(a, rec, pair, bw2, mx);
-                else { rec->cigar_len = -bw2; rec->cigar_off = mx; a.next_idx[atomicAdd(a.next_count, 1)] = pair; }
+                if (!toNext) tb_hand_over(a, rec, pair, bw2, mx);
             } else if (fallback) tb_hand_over(a, rec, pair, J.bw, (int)rec->cigar_off);
             else {
                 if (nOps > 0) {
