@@ -104,7 +104,7 @@ def _owner_main(device, req_q, resp_qs, req_names, resp_names, arena_bytes, max_
                 with sw.DeviceBatch(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend, flag=flag,
                                     device=device, filterd=0 if need_cigar else -1, ascii=True) as b:
                     b.run()
-                    rec, cig = b.fetch()
+                    rec, cig = b.fetch(cigar_cap=None if need_cigar else 1)
             else:
                 rec = np.zeros(n_all, dtype=_REC_DTYPE)
                 rec["score1"] = q_len * 1000 + r_len

@@ -535,7 +535,7 @@ def align_pairs(refs, queries, match=2, mismatch=2, gap_open=3, gap_extend=1, re
     with DeviceBatch(seqs, q_off, q_len, r_off, r_len, match, mismatch, gap_open, gap_extend, flag=flag,
                      device=device, filterd=0 if need_cigar else -1, ascii=is_ascii) as b:
         b.run()
-        rec, cig = b.fetch()
+        rec, cig = b.fetch(cigar_cap=None if need_cigar else 1)     # coordinate-only mode: no CIGAR buffer on either side
     if as_records:
         return rec, cig
     out = []
