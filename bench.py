@@ -214,6 +214,12 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+def c5_slabs_of(rank, world):
+    """which of the C5_SLABS slabs of the one C5 batch a rank owns: round robin, so every slab has exactly one owner
+    for any world size, and the statistically identical slabs make that the cost-balanced assignment"""
+    return [s for s in range(C5_SLABS) if s % world == rank]
+
+
 def make_batches(cfg_name, args, dev, rank, world):
     """the batches this rank owns (host numpy PairBatches): one for most configurations, its slabs for C5"""
     from ciri_long_b200 import workloads as W
@@ -233,7 +239,7 @@ def make_batches(cfg_name, args, dev, rank, world):
         per = n // C5_SLABS
         # the same 8 slabs whatever the number of ranks; statistically identical, so dealing them round-robin is
         # the cost-balanced (LPT) assignment
-        slabs = [W.mixed_slab_torch(per, dev, seed=W.SEED_BASE + 50 + 10 * s, params=p) for s in range(C5_SLABS) if s % world == rank]
+        slabs = [W.mixed_slab_torch(per, dev, seed=W.SEED_BASE + 50 + 10 * s, params=p) for s in c5_slabs_of(rank, world)]
         return [W.concat_batches(slabs, name="C5-mixed")]          # this rank's share as ONE batch (one set of device scratch)
     raise SystemExit("unknown config " + cfg_name)
 

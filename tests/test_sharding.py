@@ -81,3 +81,16 @@ def test_shard_batch_compacts_its_sequences():
             assert (sub["seqs"][sub["q_off"][k]:sub["q_off"][k] + sub["q_len"][k]] == b.query(i)).all()
             assert (sub["seqs"][sub["r_off"][k]:sub["r_off"][k] + sub["r_len"][k]] == b.ref(i)).all()
     assert tot == int(b.q_len.sum() + b.r_len.sum())
+
+
+def test_bench_c5_slabs_have_one_owner_each():
+    """bench.py --config C5: the same 8 slabs for every world size, each owned by exactly one rank (strong scaling)"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world in (1, 2, 3, 4, 8):
+        owned = [s for r in range(world) for s in bench.c5_slabs_of(r, world)]
+        assert sorted(owned) == list(range(bench.C5_SLABS))
+    assert {len(bench.c5_slabs_of(r, 8)) for r in range(8)} == {1}
